@@ -1,0 +1,119 @@
+/*
+ * osb200 — C ABI of the B200-native (sm_100a) hot path for Open-Sora's denoiser blocks and
+ * causal 3D VAE.  This header is the drop-in boundary: plain pointers and sizes, no torch
+ * types, no exceptions.  Each entry point cites the reference call site (path:line under the
+ * reference checkout hpcaitech/Open-Sora @ 7ad6a96) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch); the library never
+ *     allocates or frees device memory and keeps no pointer past the call;
+ *   - all work is enqueued on `stream` (a cudaStream_t / CUstream passed as void*); there are
+ *     no hidden synchronisations, so every call is CUDA-graph capturable;
+ *   - return value: 0 on success, negative osb_status on failure; osb_last_error() returns a
+ *     thread-local, human readable description of the last failure;
+ *   - bf16 tensors are row-major with an explicit leading dimension in ELEMENTS; all leading
+ *     dimensions and base pointers of GEMM operands must be 16-byte aligned.
+ */
+#ifndef OSB200_H_
+#define OSB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum osb_status {
+  OSB_OK = 0,
+  OSB_ERR_INVALID = -1,   /* bad argument (shape, alignment, null pointer) */
+  OSB_ERR_CUDA = -2,      /* CUDA runtime / driver error, see osb_last_error() */
+  OSB_ERR_UNSUPPORTED = -3,
+  OSB_ERR_NOT_INIT = -4
+} osb_status;
+
+/* ---- library management ------------------------------------------------------------------ */
+
+/* Bind to `device`, resolve cuTensorMapEncodeTiled through the runtime, opt kernels into
+ * large dynamic shared memory.  Must be called once per process and device before any op.
+ * Fails with OSB_ERR_UNSUPPORTED on anything that is not compute capability 10.x. */
+int osb_init(int device);
+int osb_version(void);
+const char* osb_last_error(void);
+/* number of kernels this library has launched since process start (bench.py's gpu_launches) */
+int64_t osb_launch_count(void);
+
+/* ---- LayerNorm (no affine) + adaLN modulate ---------------------------------------------- */
+/* y[r,:] = LN(x[r,:]) * (1 + scale[g,:]) + shift[g,:],  g = mod_index ? mod_index[r / group_rows]
+ *                                                                     : r / group_rows
+ * x,y: bf16 [rows, C] contiguous.  shift/scale: fp32, row g at shift + g*mod_stride (elements).
+ * fp32 statistics (two-pass on register-resident row), eps as given (reference: 1e-6).
+ * Replaces: opensora/models/mmdit/layers.py:205-206,223-224,248,252,312,400 (LayerNorm(no affine)
+ * followed by (1+scale)*x+shift) and upstream v1.2 STDiT3 t2i_modulate(norm(x), shift, scale)
+ * (SURVEY.md §8a-S).  C % 8 == 0, C <= 8192. */
+int osb_ln_modulate(const void* x, const float* shift, const float* scale, void* y,
+                    int64_t rows, int C, int64_t group_rows, const int32_t* mod_index,
+                    int64_t mod_stride, float eps, void* stream);
+
+/* ---- bf16 GEMM on tcgen05 with fused epilogues -------------------------------------------- */
+typedef enum osb_epilogue {
+  OSB_EPI_BIAS = 0,           /* D = A W^T + bias                                              */
+  OSB_EPI_BIAS_GELU_TANH = 1, /* D = gelu_tanh(A W^T + bias)      layers.py:277-281 (MLP[0:2]) */
+  OSB_EPI_BIAS_GATE_RES = 2   /* D = R + gate[g,:] * (A W^T + bias); gate==NULL -> plain add   */
+                              /*                      layers.py:247-252, 333-334               */
+} osb_epilogue;
+
+typedef struct osb_gemm_args {
+  const void* A;       /* bf16 [M,K], row stride lda                                            */
+  const void* W;       /* bf16 [N,K], row stride ldw  (nn.Linear.weight layout)                  */
+  const void* bias;    /* bf16 [N] or NULL                                                       */
+  void* D;             /* bf16 [M,N], row stride ldd                                             */
+  const void* R;       /* bf16 [M,N] residual (GATE_RES only), row stride ldr; may alias D       */
+  const float* gate;   /* fp32, row g at gate + g*gate_stride (GATE_RES only) or NULL            */
+  const int32_t* mod_index; /* optional indirection for g, as in osb_ln_modulate                 */
+  int64_t M, N, K;
+  int64_t lda, ldw, ldd, ldr;
+  int64_t group_rows;  /* g = row / group_rows                                                   */
+  int64_t gate_stride;
+  int32_t epilogue;    /* osb_epilogue                                                           */
+  int32_t cta_group;   /* 0 = library default, 1 = single-CTA MMA, 2 = CTA-pair MMA (cta_group::2) */
+  int32_t block_n;     /* 0 = library default, else 64/128/192/256                               */
+  int32_t reserved;
+} osb_gemm_args;
+
+/* Replaces every nn.Linear on the block path: layers.py:209,212-214 (qkv / q,k,v proj),
+ * :247,251 (attn out proj + gated residual), :277-281 (MLP), :314-333 (linear1/linear2), :401.
+ * fp32 accumulation in TMEM; epilogue math in fp32; single rounding to bf16 on store.
+ * Requires K % 8 == 0, N % 8 == 0. */
+int osb_gemm_bf16(const osb_gemm_args* args, void* stream);
+
+/* ---- attention with short key sets (whole key set resident in one CTA) -------------------- */
+typedef struct osb_attn_short_args {
+  const void* q; const void* k; const void* v; /* bf16; element (row, h*D + d) at ptr + row*ld + h*D + d */
+  void* out;                                   /* bf16 [*, out_ld], same row mapping as q        */
+  int64_t q_ld, k_ld, v_ld, out_ld;
+  /* row mapping: sequence s -> (b = s / seqs_per_batch, j = s % seqs_per_batch);
+   * q row of token t = b*q_batch_stride + j*q_seq_stride + t*q_tok_stride  (same for k/v with k_*) */
+  int64_t num_seqs, seqs_per_batch;
+  int64_t q_batch_stride, q_seq_stride, q_tok_stride;
+  int64_t k_batch_stride, k_seq_stride, k_tok_stride;
+  int32_t Lq, Lk;                 /* tokens per sequence; Lk (x sequences packed per tile) <= 320 */
+  const int32_t* kv_lens;         /* optional [num_seqs]: valid keys per sequence (<= Lk)       */
+  int32_t num_heads, head_dim;    /* head_dim: 72 (STDiT3-XL) or 64                              */
+  const void* q_norm_w;           /* bf16 [D] RMSNorm weight for q, or NULL = no QK-norm         */
+  const void* k_norm_w;           /* bf16 [D]                                                    */
+  float norm_eps;
+  const float* rope_cos;          /* fp32 [Lmax, D/2] or NULL: interleaved-pair RoPE by token    */
+  const float* rope_sin;          /*   index (rotary_embedding_torch layout)      */
+  float softmax_scale;            /* D^-0.5                                                      */
+} osb_attn_short_args;
+
+/* softmax(q k^T * scale) v per (sequence, head), non-causal, optional per-head RMSNorm on q,k
+ * and RoPE applied while staging operands into shared memory.  Replaces: mmdit/math.py:22-36
+ * (`attention`), layers.py:126-135 (QKNorm), and upstream STDiT3 Attention / MultiHeadCrossAttention
+ * (SURVEY.md §8a-S, Appendix A). */
+int osb_attn_short(const osb_attn_short_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSB200_H_ */

@@ -1,0 +1,95 @@
+// osb200 library management: init, thread-local error string, launch accounting, TMA descriptor
+// encoding through the driver entry point (no link-time dependency on libcuda).
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace osb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+static bool g_init = false;
+static int g_sms = 0;
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool initialised() { return g_init; }
+int sm_count() { return g_sms; }
+
+int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                      uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+  if (!g_encode) {
+    set_error("osb_init() has not been called");
+    return OSB_ERR_NOT_INIT;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 2) & 15)) {
+    set_error("TMA operand must be 16-byte aligned (base %p, ld %llu elements)", base,
+              (unsigned long long)ld);
+    return OSB_ERR_INVALID;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};  // bytes, dims 1..rank-1
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+                        gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %llu cols %llu ld %llu box %ux%u)",
+              (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld,
+              box_rows, box_cols);
+    return OSB_ERR_CUDA;
+  }
+  return OSB_OK;
+}
+
+int gemm_init();   // gemm_sm100.cu
+int attn_init();   // attn_short_sm100.cu
+
+}  // namespace osb
+
+extern "C" {
+
+int osb_version(void) { return 100; }
+const char* osb_last_error(void) { return osb::g_err; }
+int64_t osb_launch_count(void) { return osb::g_launches.load(); }
+
+int osb_init(int device) {
+  using namespace osb;
+  OSB_CHECK_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  OSB_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("osb200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major,
+              prop.minor);
+    return OSB_ERR_UNSUPPORTED;
+  }
+  g_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  OSB_CHECK_CUDA(cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000,
+                                                  cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return OSB_ERR_CUDA;
+  }
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  int rc = gemm_init();
+  if (rc) return rc;
+  rc = attn_init();
+  if (rc) return rc;
+  g_init = true;
+  return OSB_OK;
+}
+
+}  // extern "C"

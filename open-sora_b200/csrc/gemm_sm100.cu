@@ -1,0 +1,385 @@
+// bf16 GEMM for sm_100a:  D[M,N] = epilogue(A[M,K] * W[N,K]^T + bias)
+//
+// Persistent, warp-specialised kernel: one TMA producer warp, one tcgen05.mma issuer warp, four
+// epilogue warps.  Operands are staged by TMA into 128-byte-swizzled shared memory tiles
+// (BLOCK_K = 64 bf16 = one swizzle row), the fp32 accumulator lives in TMEM and is double
+// buffered so the epilogue of tile i overlaps the main loop of tile i+1.  kCta == 2 pairs two
+// SMs on one 256 x BLOCK_N tile (tcgen05.mma.cta_group::2): each CTA stages its own 128 rows of A
+// and half of the W tile, the leader CTA issues the MMAs for both.
+//
+// Replaces every nn.Linear on the denoiser block path of the reference
+// (opensora/models/mmdit/layers.py:209-214,247-252,277-281,314-334,401) and the fused epilogues
+// replace the separate bias / GELU(tanh) / gate*x+residual elementwise kernels.
+#include "common.cuh"
+
+namespace osb {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kNumThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kSmemBudget = 220 * 1024;
+
+struct GemmEpilogueParams {
+  const __nv_bfloat16* bias;
+  __nv_bfloat16* D;
+  const __nv_bfloat16* R;
+  const float* gate;
+  const int32_t* mod_index;
+  int64_t M, N, K;
+  int64_t ldd, ldr;
+  int64_t group_rows;
+  int64_t gate_stride;
+  int32_t epilogue;
+};
+
+template <int BLOCK_N, int kCta>
+struct GemmCfg {
+  static constexpr int LOAD_N = BLOCK_N / kCta;
+  static constexpr int A_BYTES = kBlockM * kBlockK * 2;
+  static constexpr int B_BYTES = LOAD_N * kBlockK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (kSmemBudget / STAGE_BYTES) > 8 ? 8 : (kSmemBudget / STAGE_BYTES);
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+  static constexpr uint32_t TMEM_COLS = 512;
+  static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
+  static_assert(B_BYTES % 1024 == 0, "W tile must keep 1024-byte swizzle-atom alignment");
+  static_assert(BLOCK_N % 32 == 0, "epilogue works in 32-column chunks");
+};
+
+template <int BLOCK_N, int kCta>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                 const GemmEpilogueParams p) {
+  using Cfg = GemmCfg<BLOCK_N, kCta>;
+  constexpr int kStages = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for SWIZZLE_128B tiles (the offset is identical in both CTAs of a pair)
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
+  auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (kCta == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+
+  const int64_t tile_m = (int64_t)kBlockM * kCta;
+  const int64_t num_m_blocks = (p.M + tile_m - 1) / tile_m;
+  const int64_t num_n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int64_t num_tiles = num_m_blocks * num_n_blocks;
+  const int64_t num_k_blocks = (p.K + kBlockK - 1) / kBlockK;
+  const int64_t cluster_id = blockIdx.x / kCta;
+  const int64_t num_clusters = gridDim.x / kCta;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(tmem_full_bar(s), 1);
+        mbar_init(tmem_empty_bar(s), 4 * kCta);  // one lane per epilogue warp, from every CTA of the pair
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<kCta>(tmem_slot, Cfg::TMEM_COLS);
+  }
+  tc_fence_before();
+  if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t leader_full[kStages];
+      if constexpr (kCta == 2) {
+        for (int s = 0; s < kStages; ++s)
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(leader_full[s]) : "r"(full_bar(s)), "r"(0));
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int64_t m_blk = tile / num_n_blocks, n_blk = tile % num_n_blocks;
+        const int32_t a_row = (int32_t)(m_blk * tile_m + cta_rank * kBlockM);
+        const int32_t w_row = (int32_t)(n_blk * BLOCK_N + cta_rank * Cfg::LOAD_N);
+        for (int64_t kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const int32_t k0 = (int32_t)(kb * kBlockK);
+          if constexpr (kCta == 1) {
+            mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+            tma_load_2d(&tmap_a, full_bar(stage), smem_a(stage), k0, a_row);
+            tma_load_2d(&tmap_w, full_bar(stage), smem_b(stage), k0, w_row);
+          } else {
+            if (is_leader) mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * 2);
+            tma_load_2d_cg2(&tmap_a, leader_full[stage], smem_a(stage), k0, a_row);
+            tma_load_2d_cg2(&tmap_w, leader_full[stage], smem_b(stage), k0, w_row);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (is_leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(kBlockM * kCta, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        if constexpr (kCta == 2) mbar_wait_cluster(tmem_empty_bar(as), aphase ^ 1);
+        else mbar_wait(tmem_empty_bar(as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int64_t kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a0 = smem_a(stage), b0 = smem_b(stage);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t da = make_sw128_kmajor_desc(a0 + k * 32);
+            const uint64_t db = make_sw128_kmajor_desc(b0 + k * 32);
+            umma_bf16<kCta>(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit<kCta>(empty_bar(stage));  // smem slot reusable once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit<kCta>(tmem_full_bar(as));   // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int64_t m_blk = tile / num_n_blocks, n_blk = tile % num_n_blocks;
+      const int64_t row = m_blk * tile_m + cta_rank * kBlockM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      mbar_wait(tmem_full_bar(as), aphase);
+      tc_fence_after();
+
+      const float* gate_row = nullptr;
+      if (p.epilogue == OSB_EPI_BIAS_GATE_RES && p.gate != nullptr && row_ok) {
+        int64_t g = row / p.group_rows;
+        if (p.mod_index) g = p.mod_index[g];
+        gate_row = p.gate + g * p.gate_stride;
+      }
+      __nv_bfloat16* d_row = p.D + row * p.ldd;
+      const __nv_bfloat16* r_row = p.R ? p.R + row * p.ldr : nullptr;
+
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + c0);
+        tmem_ld_32x32b_x32(taddr, v);
+        tmem_ld_wait();
+        if (c0 + 32 >= BLOCK_N) {
+          // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kCta == 2) mbar_arrive_cluster(tmem_empty_bar(as), 0);
+            else mbar_arrive(tmem_empty_bar(as));
+          }
+        }
+        const int64_t n0 = n_blk * BLOCK_N + c0;
+        if (!row_ok || n0 >= p.N) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int64_t n = n0 + j * 8;
+          if (n >= p.N) break;
+          float acc[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = __uint_as_float(v[j * 8 + e]);
+          if (p.bias) {
+            const uint4 bu = __ldg(reinterpret_cast<const uint4*>(p.bias + n));
+            const uint32_t bw[4] = {bu.x, bu.y, bu.z, bu.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_bf16x2(bw[e]);
+              acc[2 * e] += f.x;
+              acc[2 * e + 1] += f.y;
+            }
+          }
+          if (p.epilogue == OSB_EPI_BIAS_GELU_TANH) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = gelu_tanh(acc[e]);
+          } else if (p.epilogue == OSB_EPI_BIAS_GATE_RES) {
+            if (gate_row) {
+              const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate_row + n));
+              const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate_row + n + 4));
+              acc[0] *= g0.x; acc[1] *= g0.y; acc[2] *= g0.z; acc[3] *= g0.w;
+              acc[4] *= g1.x; acc[5] *= g1.y; acc[6] *= g1.z; acc[7] *= g1.w;
+            }
+            if (r_row) {
+              const uint4 ru = *reinterpret_cast<const uint4*>(r_row + n);
+              const uint32_t rw[4] = {ru.x, ru.y, ru.z, ru.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_bf16x2(rw[e]);
+                acc[2 * e] += f.x;
+                acc[2 * e + 1] += f.y;
+              }
+            }
+          }
+          uint4 o;
+          o.x = pack_bf16x2(acc[0], acc[1]);
+          o.y = pack_bf16x2(acc[2], acc[3]);
+          o.z = pack_bf16x2(acc[4], acc[5]);
+          o.w = pack_bf16x2(acc[6], acc[7]);
+          *reinterpret_cast<uint4*>(d_row + n) = o;
+        }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  // ===================== teardown =====================
+  __syncwarp();
+  tc_fence_before();
+  if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kCta>(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+template <int BLOCK_N, int kCta>
+static int launch_gemm(const osb_gemm_args& a, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N, kCta>;
+  CUtensorMap ta, tw;
+  int rc = make_tmap_2d_bf16(&ta, a.A, a.M, a.K, a.lda, kBlockM, kBlockK);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tw, a.W, a.N, a.K, a.ldw, Cfg::LOAD_N, kBlockK);
+  if (rc) return rc;
+
+  GemmEpilogueParams p;
+  p.bias = static_cast<const __nv_bfloat16*>(a.bias);
+  p.D = static_cast<__nv_bfloat16*>(a.D);
+  p.R = static_cast<const __nv_bfloat16*>(a.R);
+  p.gate = a.gate;
+  p.mod_index = a.mod_index;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.ldd = a.ldd; p.ldr = a.ldr;
+  p.group_rows = a.group_rows > 0 ? a.group_rows : a.M;
+  p.gate_stride = a.gate_stride;
+  p.epilogue = a.epilogue;
+
+  const int64_t tile_m = (int64_t)kBlockM * kCta;
+  const int64_t tiles = ((a.M + tile_m - 1) / tile_m) * ((a.N + BLOCK_N - 1) / BLOCK_N);
+  int64_t clusters = sm_count() / kCta;
+  if (tiles < clusters) clusters = tiles;
+
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * kCta));
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  OSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BLOCK_N, kCta>, ta, tw, p));
+  count_launch();
+  return OSB_OK;
+}
+
+template <int BLOCK_N, int kCta>
+static int init_one() {
+  OSB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BLOCK_N, kCta>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      GemmCfg<BLOCK_N, kCta>::SMEM_BYTES));
+  return OSB_OK;
+}
+
+int gemm_init() {
+  int rc = 0;
+  if ((rc = init_one<64, 1>())) return rc;
+  if ((rc = init_one<128, 1>())) return rc;
+  if ((rc = init_one<192, 1>())) return rc;
+  if ((rc = init_one<256, 1>())) return rc;
+  if ((rc = init_one<64, 2>())) return rc;
+  if ((rc = init_one<128, 2>())) return rc;
+  if ((rc = init_one<192, 2>())) return rc;
+  if ((rc = init_one<256, 2>())) return rc;
+  return OSB_OK;
+}
+
+// pick the tile width that minimises (waves x per-tile time); ties go to the wider tile
+static int pick_block_n(int64_t M, int64_t N, int cta) {
+  const int cands[3] = {256, 192, 128};
+  const int64_t tile_m = (int64_t)kBlockM * cta;
+  const int64_t clusters = sm_count() / cta;
+  int best = 256;
+  int64_t best_cost = INT64_MAX;
+  for (int bn : cands) {
+    const int64_t tiles = ((M + tile_m - 1) / tile_m) * ((N + bn - 1) / bn);
+    const int64_t waves = (tiles + clusters - 1) / clusters;
+    const int64_t cost = waves * bn;
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  if (N <= 64) best = 64;
+  return best;
+}
+
+}  // namespace osb
+
+extern "C" int osb_gemm_bf16(const osb_gemm_args* args, void* stream) {
+  using namespace osb;
+  if (!initialised()) { set_error("osb_init() has not been called"); return OSB_ERR_NOT_INIT; }
+  OSB_REQUIRE(args != nullptr, "osb_gemm_bf16: null args");
+  const osb_gemm_args& a = *args;
+  OSB_REQUIRE(a.A && a.W && a.D, "osb_gemm_bf16: null operand");
+  OSB_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "osb_gemm_bf16: empty problem (M %lld N %lld K %lld)",
+              (long long)a.M, (long long)a.N, (long long)a.K);
+  OSB_REQUIRE(a.K % 8 == 0 && a.N % 8 == 0, "osb_gemm_bf16: K and N must be multiples of 8 (K %lld N %lld)",
+              (long long)a.K, (long long)a.N);
+  OSB_REQUIRE(a.ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(a.D) & 15) == 0,
+              "osb_gemm_bf16: D must be 16-byte aligned with ldd %% 8 == 0");
+  OSB_REQUIRE(a.epilogue >= OSB_EPI_BIAS && a.epilogue <= OSB_EPI_BIAS_GATE_RES,
+              "osb_gemm_bf16: unknown epilogue %d", a.epilogue);
+  if (a.epilogue == OSB_EPI_BIAS_GATE_RES) {
+    OSB_REQUIRE(a.R == nullptr || (a.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(a.R) & 15) == 0),
+                "osb_gemm_bf16: R must be 16-byte aligned with ldr %% 8 == 0");
+    OSB_REQUIRE(a.gate == nullptr || (a.gate_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(a.gate) & 15) == 0),
+                "osb_gemm_bf16: gate must be 16-byte aligned with gate_stride %% 4 == 0");
+  }
+  OSB_REQUIRE(a.bias == nullptr || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0,
+              "osb_gemm_bf16: bias must be 16-byte aligned");
+  int cta = a.cta_group ? a.cta_group : 2;
+  OSB_REQUIRE(cta == 1 || cta == 2, "osb_gemm_bf16: cta_group must be 0, 1 or 2");
+  int bn = a.block_n ? a.block_n : pick_block_n(a.M, a.N, cta);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define OSB_GEMM_CASE(BN, CG) \
+  if (bn == BN && cta == CG) return launch_gemm<BN, CG>(a, s);
+  OSB_GEMM_CASE(64, 1) OSB_GEMM_CASE(128, 1) OSB_GEMM_CASE(192, 1) OSB_GEMM_CASE(256, 1)
+  OSB_GEMM_CASE(64, 2) OSB_GEMM_CASE(128, 2) OSB_GEMM_CASE(192, 2) OSB_GEMM_CASE(256, 2)
+#undef OSB_GEMM_CASE
+  set_error("osb_gemm_bf16: unsupported block_n %d", bn);
+  return OSB_ERR_UNSUPPORTED;
+}

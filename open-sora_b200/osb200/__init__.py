@@ -1,0 +1,215 @@
+"""ctypes binding of libosb200.so (the C ABI in include/osb200.h).
+
+PyTorch is used only for device memory and streams: every op takes torch CUDA tensors, passes
+raw device pointers + the current stream to the library and returns the output tensor.  There is
+NO fallback: importing without the built library, or calling an op on a non-CUDA tensor, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libosb200.so")
+
+# every symbol include/osb200.h declares (tests check the library exports all of them)
+EXPORTS = (
+    "osb_init",
+    "osb_version",
+    "osb_last_error",
+    "osb_launch_count",
+    "osb_ln_modulate",
+    "osb_gemm_bf16",
+    "osb_attn_short",
+)
+
+EPI_BIAS, EPI_BIAS_GELU_TANH, EPI_BIAS_GATE_RES = 0, 1, 2
+
+
+class OsbError(RuntimeError):
+    pass
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise OsbError(
+            f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` (nvcc, sm_100a). "
+            "osb200 has no CPU or PyTorch fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise OsbError(f"libosb200.so does not export {name}")
+    lib.osb_last_error.restype = C.c_char_p
+    lib.osb_launch_count.restype = C.c_int64
+    lib.osb_init.argtypes = [C.c_int]
+    lib.osb_ln_modulate.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p,
+        C.c_int64, C.c_float, C.c_void_p,
+    ]
+    lib.osb_gemm_bf16.argtypes = [C.c_void_p, C.c_void_p]
+    lib.osb_attn_short.argtypes = [C.c_void_p, C.c_void_p]
+    return lib
+
+
+_lib = _load()
+_initialised_devices: set[int] = set()
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("W", C.c_void_p), ("bias", C.c_void_p), ("D", C.c_void_p),
+        ("R", C.c_void_p), ("gate", C.c_void_p), ("mod_index", C.c_void_p),
+        ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
+        ("lda", C.c_int64), ("ldw", C.c_int64), ("ldd", C.c_int64), ("ldr", C.c_int64),
+        ("group_rows", C.c_int64), ("gate_stride", C.c_int64),
+        ("epilogue", C.c_int32), ("cta_group", C.c_int32), ("block_n", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class AttnShortArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p),
+        ("q_ld", C.c_int64), ("k_ld", C.c_int64), ("v_ld", C.c_int64), ("out_ld", C.c_int64),
+        ("num_seqs", C.c_int64), ("seqs_per_batch", C.c_int64),
+        ("q_batch_stride", C.c_int64), ("q_seq_stride", C.c_int64), ("q_tok_stride", C.c_int64),
+        ("k_batch_stride", C.c_int64), ("k_seq_stride", C.c_int64), ("k_tok_stride", C.c_int64),
+        ("Lq", C.c_int32), ("Lk", C.c_int32),
+        ("kv_lens", C.c_void_p),
+        ("num_heads", C.c_int32), ("head_dim", C.c_int32),
+        ("q_norm_w", C.c_void_p), ("k_norm_w", C.c_void_p),
+        ("norm_eps", C.c_float),
+        ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
+        ("softmax_scale", C.c_float),
+    ]
+
+
+def last_error() -> str:
+    return _lib.osb_last_error().decode()
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise OsbError(f"{what} failed ({rc}): {last_error()}")
+
+
+def version() -> int:
+    return _lib.osb_version()
+
+
+def launch_count() -> int:
+    return int(_lib.osb_launch_count())
+
+
+def init(device: int | None = None) -> None:
+    import torch
+
+    if not torch.cuda.is_available():
+        raise OsbError("osb200 needs a CUDA device (sm_100a); there is no CPU path")
+    if device is None:
+        device = torch.cuda.current_device()
+    if device in _initialised_devices:
+        return
+    torch.cuda.init()
+    _check(_lib.osb_init(int(device)), "osb_init")
+    _initialised_devices.add(device)
+
+
+def _stream():
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _need(t, dtype, name):
+    import torch
+
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise OsbError(f"{name} must be a CUDA tensor (osb200 has no CPU path)")
+    if t.dtype != dtype:
+        raise OsbError(f"{name} must be {dtype}, got {t.dtype}")
+    if t.dim() >= 1 and t.stride(-1) != 1 and t.shape[-1] != 1:
+        raise OsbError(f"{name} must have unit stride in the last dimension")
+    init(t.device.index)
+
+
+def ln_modulate(x, shift, scale, *, group_rows: int, mod_index=None, eps: float = 1e-6, out=None):
+    """y = LN(x) * (1 + scale[g]) + shift[g];  x bf16 [rows, C]; shift/scale fp32 [G, C] views."""
+    import torch
+
+    _need(x, torch.bfloat16, "x"); _need(shift, torch.float32, "shift"); _need(scale, torch.float32, "scale")
+    _need(mod_index, torch.int32, "mod_index")
+    assert x.dim() == 2 and x.is_contiguous()
+    assert shift.dim() == 2 and scale.dim() == 2 and shift.stride(0) == scale.stride(0)
+    rows, Cdim = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _check(_lib.osb_ln_modulate(_ptr(x), _ptr(shift), _ptr(scale), _ptr(out), rows, Cdim, group_rows,
+                                _ptr(mod_index), shift.stride(0), eps, _stream()), "osb_ln_modulate")
+    return out
+
+
+def gemm(a, w, bias=None, *, epilogue: int = EPI_BIAS, residual=None, gate=None, group_rows: int = 0,
+         mod_index=None, out=None, cta_group: int = 0, block_n: int = 0):
+    """out = epilogue(a @ w.T + bias).  a bf16 [M,K] (row stride free), w bf16 [N,K], bias bf16 [N].
+    GATE_RES: out = residual + gate[g] * (a @ w.T + bias), gate fp32 [G, N] view, may be None."""
+    import torch
+
+    _need(a, torch.bfloat16, "a"); _need(w, torch.bfloat16, "w"); _need(bias, torch.bfloat16, "bias")
+    _need(residual, torch.bfloat16, "residual"); _need(gate, torch.float32, "gate")
+    _need(mod_index, torch.int32, "mod_index")
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    _need(out, torch.bfloat16, "out")
+    args = GemmArgs()
+    args.A, args.W, args.bias, args.D = a.data_ptr(), w.data_ptr(), (bias.data_ptr() if bias is not None else None), out.data_ptr()
+    args.R = residual.data_ptr() if residual is not None else None
+    args.gate = gate.data_ptr() if gate is not None else None
+    args.mod_index = mod_index.data_ptr() if mod_index is not None else None
+    args.M, args.N, args.K = M, N, K
+    args.lda, args.ldw, args.ldd = a.stride(0), w.stride(0), out.stride(0)
+    args.ldr = residual.stride(0) if residual is not None else 0
+    args.group_rows = group_rows if group_rows > 0 else M
+    args.gate_stride = gate.stride(0) if gate is not None else 0
+    args.epilogue, args.cta_group, args.block_n = epilogue, cta_group, block_n
+    _check(_lib.osb_gemm_bf16(C.byref(args), _stream()), "osb_gemm_bf16")
+    return out
+
+
+def attn_short(q, k, v, out, *, num_seqs: int, seqs_per_batch: int, q_strides, k_strides, Lq: int, Lk: int,
+               num_heads: int, head_dim: int, kv_lens=None, q_norm_w=None, k_norm_w=None, norm_eps: float = 1e-6,
+               rope_cos=None, rope_sin=None, softmax_scale: float | None = None):
+    """softmax(q k^T * scale) v per (sequence, head) with optional fused QK-RMSNorm and RoPE.
+    q/k/v/out are 2-D bf16 views [rows, ld]; *_strides = (batch, seq, token) strides in rows."""
+    import torch
+
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out"), (q_norm_w, "q_norm_w"), (k_norm_w, "k_norm_w")):
+        _need(t, torch.bfloat16, n)
+    _need(rope_cos, torch.float32, "rope_cos"); _need(rope_sin, torch.float32, "rope_sin")
+    _need(kv_lens, torch.int32, "kv_lens")
+    a = AttnShortArgs()
+    a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.q_ld, a.k_ld, a.v_ld, a.out_ld = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
+    a.num_seqs, a.seqs_per_batch = num_seqs, seqs_per_batch
+    a.q_batch_stride, a.q_seq_stride, a.q_tok_stride = q_strides
+    a.k_batch_stride, a.k_seq_stride, a.k_tok_stride = k_strides
+    a.Lq, a.Lk = Lq, Lk
+    a.kv_lens = kv_lens.data_ptr() if kv_lens is not None else None
+    a.num_heads, a.head_dim = num_heads, head_dim
+    a.q_norm_w = q_norm_w.data_ptr() if q_norm_w is not None else None
+    a.k_norm_w = k_norm_w.data_ptr() if k_norm_w is not None else None
+    a.norm_eps = norm_eps
+    a.rope_cos = rope_cos.data_ptr() if rope_cos is not None else None
+    a.rope_sin = rope_sin.data_ptr() if rope_sin is not None else None
+    a.softmax_scale = softmax_scale if softmax_scale is not None else head_dim ** -0.5
+    _check(_lib.osb_attn_short(C.byref(a), _stream()), "osb_attn_short")
+    return out
