@@ -1,0 +1,100 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/osb200.h declares, and the product path refuses to run without a GPU (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "osb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(osb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import osb200
+
+    declared = _header_symbols()
+    assert declared, "no entry points parsed from include/osb200.h"
+    lib = ctypes.CDLL(osb200.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"libosb200.so does not export {name}"
+    assert sorted(osb200.EXPORTS) == declared
+
+
+def test_version_and_error_string_without_gpu():
+    import osb200
+
+    assert osb200.version() >= 100
+    assert isinstance(osb200.last_error(), str)
+    assert osb200.launch_count() >= 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_ops_fail_loudly_without_gpu():
+    import osb200
+
+    with pytest.raises(osb200.OsbError):
+        osb200.init()
+    a = torch.zeros(8, 8, dtype=torch.bfloat16)
+    with pytest.raises(osb200.OsbError):
+        osb200.gemm(a, a)
+    # calling the C entry point directly before osb_init must return an error code, not crash
+    args = osb200.GemmArgs()
+    rc = osb200._lib.osb_gemm_bf16(ctypes.byref(args), None)
+    assert rc != 0 and "osb_init" in osb200.last_error()
+
+
+def test_ctypes_struct_layout_matches_header():
+    """sizeof of the ctypes mirrors must equal the C structs (checked against a gcc-compiled probe)."""
+    import subprocess
+    import tempfile
+
+    import osb200
+
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "probe.c")
+        with open(src, "w") as f:
+            f.write('#include <stdio.h>\n#include <stddef.h>\n#include "osb200.h"\nint main(){printf("%zu %zu %zu %zu\\n",'
+                    "sizeof(osb_gemm_args), sizeof(osb_attn_short_args), offsetof(osb_gemm_args, epilogue),"
+                    "offsetof(osb_attn_short_args, softmax_scale));return 0;}\n")
+        exe = os.path.join(d, "probe")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        sizes = [int(v) for v in subprocess.check_output([exe]).split()]
+    assert ctypes.sizeof(osb200.GemmArgs) == sizes[0]
+    assert ctypes.sizeof(osb200.AttnShortArgs) == sizes[1]
+    assert osb200.GemmArgs.epilogue.offset == sizes[2]
+    assert osb200.AttnShortArgs.softmax_scale.offset == sizes[3]
+
+
+def test_registry_and_state_dict_contract():
+    from opensora.registry import MODELS, build_module
+    from oracle.stdit3_oracle import STDiT3 as Oracle, STDiT3_XS_2_config
+
+    m = build_module(dict(type="STDiT3-XS/2"), MODELS)
+    o = Oracle(STDiT3_XS_2_config())
+    a, b = m.state_dict(), o.state_dict()
+    assert set(a) == set(b)
+    assert all(a[k].shape == b[k].shape for k in a)
+    assert "STDiT3-XL/2" in MODELS and "STDiT3-3B/2" in MODELS
+    xl = build_module(dict(type="STDiT3-XL/2", depth=1), MODELS)  # kwargs override like the reference's factories
+    assert xl.hidden_size == 1152 and xl.num_heads == 16 and xl.depth == 1
+    assert build_module(m, MODELS) is m and build_module(None, MODELS) is None
+    with pytest.raises(TypeError):
+        build_module(3, MODELS)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_model_forward_has_no_cpu_fallback():
+    import osb200
+    from opensora.models.stdit.stdit3 import STDiT3_XS_2
+
+    m = STDiT3_XS_2()
+    with pytest.raises(osb200.OsbError):
+        m(torch.zeros(1, 4, 2, 4, 4), torch.zeros(1), torch.zeros(1, 1, 300, 4096), fps=torch.ones(1),
+          height=torch.ones(1), width=torch.ones(1))
