@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py — denoise-steps/s of STDiT3-XL/2 (bf16) on a 64x32x32 latent, BASELINE.json's metric.
+
+One "step" = one denoiser forward on one synthetic latent [1,4,64,32,32] with T5 embeddings
+[1,1,300,4096] (36.13 algorithmic TFLOP) through the osb200 sm_100a path.
+
+    python bench.py --gpus N --steps K --warmup W          # our arm (N>1 under torchrun)
+    python bench.py --impl reference ...                   # the reference's CPU arithmetic (oracle port)
+
+JSON line keys follow the driver's contract: `value` is device-resident throughput, `e2e` is the same
+metric through the public model API with pinned-host inputs copied in and the result copied out
+inside the timed region, `roofline` is the dominant kernel family (tcgen05 GEMM) measured live with
+CUDA events on the launching stream, `cpu_baseline` is the oracle timed on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "open-sora_b200"))
+
+import torch  # noqa: E402
+
+METRIC = "denoise-steps/sec STDiT3-XL/2 64x32x32 bf16"
+UNIT = "steps/s"
+T_LAT, H_LAT, W_LAT = 64, 32, 32
+FLOP_PER_STEP = 36.13e12  # BASELINE.md §3 / SURVEY.md §8d, per sample per forward
+
+
+def algorithmic_flops(depth=28, C=1152, T=64, S=256, Ly=300):
+    N = T * S
+    return depth * (2 * (28 * N * C * C + 4 * Ly * C * C) + 4 * N * C * (S + T + 2 * Ly))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(burst=d.get("bf16_tflops"), sustained=d.get("bf16_tflops_sustained"), hbm=d.get("hbm_gbs"), src="measured")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (restatement of the reference arithmetic) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step(sample_seconds_budget: float = 20.0):
+    """Times ONE spatial+temporal block pair of the fp32 oracle at the full 16384 tokens plus the
+    embedders/final layer, and extrapolates to the 28 pairs of a step (linear in depth, exact: the
+    blocks are identical in shape).  Returns (steps_per_s, cores, sample description)."""
+    from oracle import stdit3_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.STDiT3_XL_2_config()
+    cfg.depth = 1
+    m = O.STDiT3(cfg).eval()
+    O.init_synthetic_weights(m)
+    inp = O.synthetic_inputs(cfg, 1, T_LAT, H_LAT, W_LAT)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        m(**inp)
+        t_full1 = time.perf_counter() - t0  # depth-1 model: embed + 1 pair + final
+        # isolate the pair: time the two blocks alone on the embedded tokens
+        B, T, S, C = 1, T_LAT, (H_LAT // 2) * (W_LAT // 2), cfg.hidden_size
+        x = torch.randn(B, T * S, C)
+        t_mlp = torch.randn(B, 6 * C)
+        y, y_lens = m.encode_text(inp["y"], inp["mask"])
+        t0 = time.perf_counter()
+        x = m.spatial_blocks[0](x, y, t_mlp, y_lens, None, None, T, S)
+        x = m.temporal_blocks[0](x, y, t_mlp, y_lens, None, None, T, S)
+        t_pair = time.perf_counter() - t0
+    t_other = max(t_full1 - t_pair, 0.0)
+    step_s = 28 * t_pair + t_other
+    return 1.0 / step_s, cores, (f"1 of 28 spatial+temporal block pairs of the fp32 oracle timed at the full 16384 tokens "
+                                 f"({t_pair:.2f}s) + embedders/final ({t_other:.2f}s), x28 extrapolated")
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    vals = []
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        v, cores, sample = cpu_reference_step()
+        if i >= args.warmup:
+            vals.append(v)
+    v = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "STDiT3-XL/2 one denoise forward, latent 1x4x64x32x32, text 300x4096 (CPU oracle port; "
+                               "STDiT3 is absent from the reference checkout, SURVEY.md §0)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def build_model(device):
+    from opensora.registry import MODELS, build_module
+
+    torch.manual_seed(1234)
+    m = build_module(dict(type="STDiT3-XL/2"), MODELS).eval()
+    g = torch.Generator().manual_seed(1234)
+    with torch.no_grad():  # random-init weights of the named architecture (no checkpoints offline)
+        for n, p in m.named_parameters():
+            if p.dim() >= 2 and "scale_shift_table" not in n:
+                p.copy_(torch.randn(p.shape, generator=g) * (0.7 / (p[0].numel() ** 0.5)))
+            elif n.endswith("bias"):
+                p.copy_(0.02 * torch.randn(p.shape, generator=g))
+    return m.to(device=device, dtype=torch.bfloat16)
+
+
+def host_inputs(seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(1, 4, T_LAT, H_LAT, W_LAT, generator=g).pin_memory()
+    y = torch.randn(1, 1, 300, 4096, generator=g).to(torch.bfloat16).pin_memory()
+    mask = torch.ones(1, 300, dtype=torch.int64)
+    mask[0, 260:] = 0
+    return dict(x=x, timestep=torch.tensor([500.0]).pin_memory(), y=y, mask=mask.pin_memory(), fps=torch.tensor([24.0]),
+                height=torch.tensor([256.0]), width=torch.tensor([256.0]))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="osb200", choices=["osb200", "reference"])
+    ap.add_argument("--parallel", default="sp", choices=["sp", "dp"],
+                    help="N>1: sp = one sample sequence-sharded over ranks (strong scaling, north_star scheme); "
+                         "dp = one sample per rank (weak scaling, no collective)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "osb200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+
+    import osb200
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    osb200.init(local_rank)
+    model = build_model(dev)
+    mode = args.parallel if world > 1 else "single"
+    if mode == "sp":
+        model.enable_sequence_parallel(dist.group.WORLD)
+    hin = host_inputs(4321 + (rank if mode == "dp" else 0))
+    din = {k: v.to(dev, non_blocking=True) for k, v in hin.items()}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    out_holder = {}
+
+    def step_resident():
+        with torch.no_grad():
+            out_holder["o"] = model(**din)
+
+    h2d = sum(v.numel() * v.element_size() for k, v in hin.items() if k in ("x", "timestep", "y", "mask"))
+    host_out = torch.empty(1, 8, T_LAT, H_LAT, W_LAT, dtype=torch.float32).pin_memory()
+
+    def step_e2e():  # the call a user makes: host tensors in, host tensor out
+        with torch.no_grad():
+            d = {k: v.to(dev, non_blocking=True) for k, v in hin.items()}
+            o = model(**d)
+            host_out.copy_(o, non_blocking=True)
+
+    for _ in range(args.warmup):
+        step_resident()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = osb200.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = osb200.launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # ---- roofline leg: per-launch CUDA-event timing of every kernel family over one more pass ------
+    osb200.start_profile()
+    for _ in range(2):
+        step_resident()
+    rec = osb200.stop_profile()
+    fam = {}
+    for name, work, t in rec:
+        f = fam.setdefault(name, [0.0, 0.0, 0])
+        f[0] += work
+        f[1] += t
+        f[2] += 1
+
+    units = args.steps * (world if mode == "dp" else 1)
+    value = units / (ms / 1e3)
+    e2e = units / (ms_e2e / 1e3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    g = fam.get("gemm", [0.0, 1.0, 1])
+    gemm_tflops = g[0] / (g[1] * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (all %d launches of a step, FLOP-weighted)" % (g[2] // 2),
+            "achieved": gemm_tflops, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": gemm_tflops / pk["sustained"],
+            "peak_kind": f"bf16_tflops_sustained of {pk['src']} (burst {pk['burst']})", "traffic": traffic,
+            "step_frac_of_peak": (FLOP_PER_STEP * value / (world if mode == 'dp' else 1) / 1e12) / pk["sustained"] / (world if mode == 'sp' else 1),
+            "families": {k: {"launches_per_step": v[2] // 2, "ms_per_step": v[1] / 2,
+                             ("tflops" if k != "ln_modulate" else "gbs"): (v[0] / (v[1] * 1e-3) / (1e12 if k != "ln_modulate" else 1e9))}
+                         for k, v in fam.items()}}
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        v, cores, sample = cpu_reference_step()
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if mode == "dp" else "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic (seeded N(0,1) latents / T5 embeddings, random-init weights)",
+        "config": {"workload": "STDiT3-XL/2 (depth 28x2, C=1152, 16x72 heads) one denoise forward, latent 1x4x64x32x32 "
+                               "(T=64,S=256), text 300x4096 (260 valid)", "parallelism": mode + str(world),
+                   "l2": "weights 2.2 GB + activations stream through every step (>> 126 MB L2): inputs larger than L2",
+                   "algorithmic_tflop_per_step": FLOP_PER_STEP / 1e12},
+        "clocks": clk, "gpu_launches": launches,
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_out.numel() * 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

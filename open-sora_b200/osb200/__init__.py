@@ -55,6 +55,46 @@ def _load() -> C.CDLL:
 _lib = _load()
 _initialised_devices: set[int] = set()
 
+# Optional per-launch device timing (bench.py's roofline leg): when a list is installed with
+# start_profile(), every op brackets its launch with CUDA events on the launching stream and appends
+# (kernel family, algorithmic work, start_event, end_event).  Off (None) in normal operation.
+_profile: list | None = None
+
+
+def start_profile() -> None:
+    global _profile
+    _profile = []
+
+
+def stop_profile() -> list:
+    """Returns [(family, work, milliseconds)] after synchronising."""
+    global _profile
+    import torch
+
+    torch.cuda.synchronize()
+    rec, _profile = _profile or [], None
+    return [(n, w, s.elapsed_time(e)) for (n, w, s, e) in rec]
+
+
+class _Timed:
+    def __init__(self, family: str, work: float):
+        self.family, self.work = family, work
+
+    def __enter__(self):
+        if _profile is not None:
+            import torch
+
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _profile is not None:
+            self.e.record()
+            _profile.append((self.family, self.work, self.s, self.e))
+        return False
+
 
 class GemmArgs(C.Structure):
     _fields_ = [
@@ -150,8 +190,9 @@ def ln_modulate(x, shift, scale, *, group_rows: int, mod_index=None, eps: float 
     rows, Cdim = x.shape
     if out is None:
         out = torch.empty_like(x)
-    _check(_lib.osb_ln_modulate(_ptr(x), _ptr(shift), _ptr(scale), _ptr(out), rows, Cdim, group_rows,
-                                _ptr(mod_index), shift.stride(0), eps, _stream()), "osb_ln_modulate")
+    with _Timed("ln_modulate", 4.0 * rows * Cdim):  # algorithmic bytes: read x + write y (bf16)
+        _check(_lib.osb_ln_modulate(_ptr(x), _ptr(shift), _ptr(scale), _ptr(out), rows, Cdim, group_rows,
+                                    _ptr(mod_index), shift.stride(0), eps, _stream()), "osb_ln_modulate")
     return out
 
 
@@ -181,7 +222,8 @@ def gemm(a, w, bias=None, *, epilogue: int = EPI_BIAS, residual=None, gate=None,
     args.group_rows = group_rows if group_rows > 0 else M
     args.gate_stride = gate.stride(0) if gate is not None else 0
     args.epilogue, args.cta_group, args.block_n = epilogue, cta_group, block_n
-    _check(_lib.osb_gemm_bf16(C.byref(args), _stream()), "osb_gemm_bf16")
+    with _Timed("gemm", 2.0 * M * N * K):  # algorithmic FLOPs
+        _check(_lib.osb_gemm_bf16(C.byref(args), _stream()), "osb_gemm_bf16")
     return out
 
 
@@ -211,5 +253,6 @@ def attn_short(q, k, v, out, *, num_seqs: int, seqs_per_batch: int, q_strides, k
     a.rope_cos = rope_cos.data_ptr() if rope_cos is not None else None
     a.rope_sin = rope_sin.data_ptr() if rope_sin is not None else None
     a.softmax_scale = softmax_scale if softmax_scale is not None else head_dim ** -0.5
-    _check(_lib.osb_attn_short(C.byref(a), _stream()), "osb_attn_short")
+    with _Timed("attn_short", 4.0 * num_seqs * Lq * Lk * num_heads * head_dim):  # QK^T + PV FLOPs
+        _check(_lib.osb_attn_short(C.byref(a), _stream()), "osb_attn_short")
     return out
