@@ -17,7 +17,9 @@ namespace osb {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kNumThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
-constexpr int kSmemBudget = 220 * 1024;
+constexpr int kStagePitch = 68;                      // floats per staged row: 64 columns + 4 pad (bank spread)
+constexpr int kEpiStageBytes = 4 * 32 * kStagePitch * 4;  // one [32 x 64] fp32 tile per epilogue warp
+constexpr int kSmemBudget = 224 * 1024 - kEpiStageBytes;
 
 struct GemmEpilogueParams {
   const __nv_bfloat16* bias;
@@ -40,11 +42,12 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (kSmemBudget / STAGE_BYTES) > 8 ? 8 : (kSmemBudget / STAGE_BYTES);
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + kEpiStageBytes + 1024;  // +1024 alignment slack
   static constexpr uint32_t TMEM_COLS = 512;
   static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
   static_assert(B_BYTES % 1024 == 0, "W tile must keep 1024-byte swizzle-atom alignment");
-  static_assert(BLOCK_N % 32 == 0, "epilogue works in 32-column chunks");
+  static_assert(BLOCK_N % 64 == 0, "epilogue works in 64-column chunks");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 template <int BLOCK_N, int kCta>
@@ -63,6 +66,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
   auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  const uint32_t stage_base = bar_base + Cfg::BAR_BYTES;  // epilogue staging tiles (16-byte aligned)
   auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
   auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
 
@@ -167,32 +171,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else {
     // ===================== epilogue warps =====================
+    // TMEM -> registers (thread = accumulator row) -> per-warp fp32 staging tile in smem -> re-read
+    // with a row-contiguous mapping so that residual loads and output stores are coalesced
+    // (4 rows x 128 B per warp instruction) instead of 32 scattered rows.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    float* stage_w = reinterpret_cast<float*>(smem_raw + (stage_base - smem_u32(smem_raw))) + q * (32 * kStagePitch);
     int as = 0;
     uint32_t aphase = 0;
+    const uint32_t group_rows32 = (uint32_t)(p.group_rows > 0xffffffffll ? 0xffffffffu : p.group_rows);
     for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int64_t m_blk = tile / num_n_blocks, n_blk = tile % num_n_blocks;
-      const int64_t row = m_blk * tile_m + cta_rank * kBlockM + q * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int64_t row0 = m_blk * tile_m + cta_rank * kBlockM + q * 32;  // first row of this warp
       mbar_wait(tmem_full_bar(as), aphase);
       tc_fence_after();
 
-      const float* gate_row = nullptr;
-      if (p.epilogue == OSB_EPI_BIAS_GATE_RES && p.gate != nullptr && row_ok) {
-        int64_t g = row / p.group_rows;
-        if (p.mod_index) g = p.mod_index[g];
-        gate_row = p.gate + g * p.gate_stride;
-      }
-      __nv_bfloat16* d_row = p.D + row * p.ldd;
-      const __nv_bfloat16* r_row = p.R ? p.R + row * p.ldr : nullptr;
-
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t v[32];
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {
+        uint32_t v[64];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + c0);
-        tmem_ld_32x32b_x32(taddr, v);
+        tmem_ld_32x32b_x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld_32x32b_x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
         tmem_ld_wait();
-        if (c0 + 32 >= BLOCK_N) {
+        if (c0 + 64 >= BLOCK_N) {
           // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -202,52 +202,66 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
         const int64_t n0 = n_blk * BLOCK_N + c0;
-        if (!row_ok || n0 >= p.N) continue;
+        if (row0 >= p.M || n0 >= p.N) continue;   // warp-uniform
+        float4* my = reinterpret_cast<float4*>(stage_w + lane * kStagePitch);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int64_t n = n0 + j * 8;
-          if (n >= p.N) break;
-          float acc[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = __uint_as_float(v[j * 8 + e]);
-          if (p.bias) {
-            const uint4 bu = __ldg(reinterpret_cast<const uint4*>(p.bias + n));
-            const uint32_t bw[4] = {bu.x, bu.y, bu.z, bu.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = unpack_bf16x2(bw[e]);
-              acc[2 * e] += f.x;
-              acc[2 * e + 1] += f.y;
-            }
-          }
-          if (p.epilogue == OSB_EPI_BIAS_GELU_TANH) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = gelu_tanh(acc[e]);
-          } else if (p.epilogue == OSB_EPI_BIAS_GATE_RES) {
-            if (gate_row) {
-              const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate_row + n));
-              const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate_row + n + 4));
-              acc[0] *= g0.x; acc[1] *= g0.y; acc[2] *= g0.z; acc[3] *= g0.w;
-              acc[4] *= g1.x; acc[5] *= g1.y; acc[6] *= g1.z; acc[7] *= g1.w;
-            }
-            if (r_row) {
-              const uint4 ru = *reinterpret_cast<const uint4*>(r_row + n);
-              const uint32_t rw[4] = {ru.x, ru.y, ru.z, ru.w};
+        for (int j = 0; j < 16; ++j)
+          my[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        __syncwarp();
+#pragma unroll 2
+        for (int it = 0; it < 8; ++it) {
+          const int i = it * 32 + lane;
+          const int rr = i >> 3, g8 = i & 7;
+          const int64_t row = row0 + rr;
+          const int64_t n = n0 + g8 * 8;
+          if (row < p.M && n < p.N) {
+            const float4 a0 = *reinterpret_cast<const float4*>(stage_w + rr * kStagePitch + g8 * 8);
+            const float4 a1 = *reinterpret_cast<const float4*>(stage_w + rr * kStagePitch + g8 * 8 + 4);
+            float acc[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            if (p.bias) {
+              const uint4 bu = __ldg(reinterpret_cast<const uint4*>(p.bias + n));
+              const uint32_t bw[4] = {bu.x, bu.y, bu.z, bu.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 f = unpack_bf16x2(rw[e]);
+                const float2 f = unpack_bf16x2(bw[e]);
                 acc[2 * e] += f.x;
                 acc[2 * e + 1] += f.y;
               }
             }
+            if (p.epilogue == OSB_EPI_BIAS_GELU_TANH) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[e] = gelu_tanh(acc[e]);
+            } else if (p.epilogue == OSB_EPI_BIAS_GATE_RES) {
+              if (p.gate != nullptr) {
+                int64_t gi = (uint32_t)row / group_rows32;
+                if (p.mod_index) gi = p.mod_index[gi];
+                const float* gate_row = p.gate + gi * p.gate_stride + n;
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate_row));
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate_row + 4));
+                acc[0] *= g0.x; acc[1] *= g0.y; acc[2] *= g0.z; acc[3] *= g0.w;
+                acc[4] *= g1.x; acc[5] *= g1.y; acc[6] *= g1.z; acc[7] *= g1.w;
+              }
+              if (p.R != nullptr) {
+                const uint4 ru = *reinterpret_cast<const uint4*>(p.R + row * p.ldr + n);
+                const uint32_t rw[4] = {ru.x, ru.y, ru.z, ru.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = unpack_bf16x2(rw[e]);
+                  acc[2 * e] += f.x;
+                  acc[2 * e + 1] += f.y;
+                }
+              }
+            }
+            uint4 o;
+            o.x = pack_bf16x2(acc[0], acc[1]);
+            o.y = pack_bf16x2(acc[2], acc[3]);
+            o.z = pack_bf16x2(acc[4], acc[5]);
+            o.w = pack_bf16x2(acc[6], acc[7]);
+            *reinterpret_cast<uint4*>(p.D + row * p.ldd + n) = o;
           }
-          uint4 o;
-          o.x = pack_bf16x2(acc[0], acc[1]);
-          o.y = pack_bf16x2(acc[2], acc[3]);
-          o.z = pack_bf16x2(acc[4], acc[5]);
-          o.w = pack_bf16x2(acc[6], acc[7]);
-          *reinterpret_cast<uint4*>(d_row + n) = o;
         }
+        __syncwarp();  // staging tile is reused by the next chunk
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }

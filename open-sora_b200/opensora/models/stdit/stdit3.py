@@ -22,6 +22,7 @@ import os
 from dataclasses import asdict, dataclass
 
 import torch
+import torch.distributed as dist
 import torch.nn as nn
 
 from opensora.registry import MODELS
@@ -261,7 +262,20 @@ class STDiT3(nn.Module):
             x = torch.nn.functional.pad(x, (0, -Wx % pw, 0, -Hx % ph, 0, -Tx % pt))
         T, H, W = self.get_dynamic_size(x)
         S = H * W
-        N = T * S
+        # sequence parallelism: this rank owns frames [t0, t0+Tl) for every token-local op
+        sp = self._sp_group
+        P = dist.get_world_size(sp) if sp is not None else 1
+        if P > 1:
+            if T % P or S % P:
+                raise ValueError(f"sequence parallel needs T ({T}) and S ({S}) divisible by the group size {P}")
+            Tl = T // P
+            t0 = dist.get_rank(sp) * Tl
+            x = x[:, :, t0 * pt:(t0 + Tl) * pt]
+            if x_mask is not None:
+                x_mask = x_mask.reshape(B, T)[:, t0:t0 + Tl]
+        else:
+            Tl = T
+        N = Tl * S  # local tokens per sample
         scale = (float(height[0]) * float(width[0])) ** 0.5 / self.input_sq_size
         pos = self._pos_embed(H, W, scale, round(S**0.5), dev)
 
@@ -284,7 +298,7 @@ class STDiT3(nn.Module):
         mod_index = None
         group_rows = N
         if x_mask is not None:
-            xm = x_mask.to(dev).bool().reshape(B, T)
+            xm = x_mask.to(dev).bool().reshape(B, Tl)
             base = torch.arange(B, device=dev, dtype=torch.int32)[:, None]
             mod_index = torch.where(xm, base, base + B).to(torch.int32).reshape(-1).contiguous()
             group_rows = S
@@ -307,7 +321,7 @@ class STDiT3(nn.Module):
             kv_lens = None
 
         # ---- patch embedding (conv with kernel == stride  ==  GEMM over patch vectors) + pos_embed ---
-        xp = x.view(B, Cin, T, pt, H, ph, W, pw).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(B * N, Cin * pt * ph * pw)
+        xp = x.reshape(B, Cin, Tl, pt, H, ph, W, pw).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(B * N, Cin * pt * ph * pw)
         Kp = xp.shape[1]
         if Kp % 8:
             xp = torch.nn.functional.pad(xp, (0, -Kp % 8))
@@ -315,14 +329,7 @@ class STDiT3(nn.Module):
         else:
             xw = cst["x_w"]
         xs = osb.gemm(xp.contiguous(), xw, self.x_embedder.proj.bias)                    # [B*N, C]
-        xs = (xs.view(B * T, S, C) + pos[None]).view(B * N, C)
-
-        sp = self._sp_group
-        if sp is not None:
-            from opensora.acceleration.sequence_parallel import STDiT3SequenceParallel
-
-            return STDiT3SequenceParallel(self, sp).run(xs, B, T, S, H, W, Tx, Hx, Wx, mod, fmod, mod_index, group_rows,
-                                                         kv_all, kv_lens, Ly)
+        xs = (xs.view(B * Tl, S, C) + pos[None]).view(B * N, C)
 
         # ---- workspaces reused by every block ------------------------------------------------------
         R = B * N
@@ -339,13 +346,17 @@ class STDiT3(nn.Module):
             for blk in (sb, tb):
                 m = mod[:, bi]  # [B', 6, C] view, row stride = mod.stride(0)
                 self._block(osb, blk, xs, m, mod_index, group_rows, kv_all[:, bi * 2 * C:(bi + 1) * 2 * C], kv_lens, Ly,
-                            B, T, S, xm_buf, qkv, ao, qc, hid, cos, sin)
+                            B, T, Tl, S, xm_buf, qkv, ao, qc, hid, cos, sin, sp if P > 1 else None)
                 bi += 1
 
         # ---- final layer + unpatchify -----------------------------------------------------------------
         osb.ln_modulate(xs, fmod[:, 0], fmod[:, 1], group_rows=group_rows, mod_index=mod_index, out=xm_buf)
         fl = self.final_layer.linear
         o = osb.gemm(xm_buf, fl.weight, fl.bias)                                         # [B*N, pt*ph*pw*Cout]
+        if P > 1:  # exit all-gather of the T shards (communications.py gather_forward_split_backward)
+            from opensora.acceleration.communications import gather_forward_split_backward
+
+            o = gather_forward_split_backward(o.view(B, Tl, S, -1), sp, dim=1).reshape(B * T * S, -1)
         return self._unpatchify(o, B, T, H, W, Tx, Hx, Wx)
 
     def _unpatchify(self, o, B, T, H, W, Tx, Hx, Wx):
@@ -354,23 +365,37 @@ class STDiT3(nn.Module):
         o = o.reshape(B, self.out_channels, T * pt, H * ph, W * pw)[:, :, :Tx, :Hx, :Wx]
         return o.to(torch.float32)
 
-    def _block(self, osb, blk, xs, m, mod_index, group_rows, kv, kv_lens, Ly, B, T, S, xm_buf, qkv, ao, qc, hid, cos, sin):
+    def _block(self, osb, blk, xs, m, mod_index, group_rows, kv, kv_lens, Ly, B, T, Tl, S, xm_buf, qkv, ao, qc, hid, cos,
+               sin, sp):
         C, Hh, D = self.hidden_size, self.num_heads, self.head_dim
-        N = T * S
+        N = Tl * S
         a, ca, mlp = blk.attn, blk.cross_attn, blk.mlp
         qn = a.q_norm.weight if isinstance(a.q_norm, _Norm) else None
         kn = a.k_norm.weight if isinstance(a.k_norm, _Norm) else None
         # 1. self attention (spatial: sequences over S; temporal: sequences over T with RoPE)
         osb.ln_modulate(xs, m[:, 0], m[:, 1], group_rows=group_rows, mod_index=mod_index, out=xm_buf)
-        osb.gemm(xm_buf, a.qkv.weight, a.qkv.bias, out=qkv)
         if blk.temporal:
-            strides = (N, 1, S)
-            osb.attn_short(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], ao, num_seqs=B * S, seqs_per_batch=S,
+            if sp is not None:
+                # T-sharded -> S-sharded transposition (all-to-all over NVLink), attention over the full T
+                # for this rank's S/P columns, and back.  Rows stay B*T*S/P on both sides.
+                from opensora.acceleration.communications import all_to_all
+
+                Sl = S // (T // Tl)
+                xt = all_to_all(xm_buf.view(B, Tl, S, C), sp, scatter_dim=2, gather_dim=1).view(B * T * Sl, C)
+            else:
+                Sl, xt = S, xm_buf
+            osb.gemm(xt, a.qkv.weight, a.qkv.bias, out=qkv)
+            strides = (T * Sl, 1, Sl)
+            ao_t = ao if sp is None else torch.empty_like(ao)
+            osb.attn_short(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], ao_t, num_seqs=B * Sl, seqs_per_batch=Sl,
                            q_strides=strides, k_strides=strides, Lq=T, Lk=T, num_heads=Hh, head_dim=D,
                            q_norm_w=qn, k_norm_w=kn, rope_cos=cos, rope_sin=sin)
+            if sp is not None:
+                ao = all_to_all(ao_t.view(B, T, Sl, C), sp, scatter_dim=1, gather_dim=2).view(B * N, C)
         else:
+            osb.gemm(xm_buf, a.qkv.weight, a.qkv.bias, out=qkv)
             strides = (N, S, 1)
-            osb.attn_short(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], ao, num_seqs=B * T, seqs_per_batch=T,
+            osb.attn_short(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], ao, num_seqs=B * Tl, seqs_per_batch=Tl,
                            q_strides=strides, k_strides=strides, Lq=S, Lk=S, num_heads=Hh, head_dim=D,
                            q_norm_w=qn, k_norm_w=kn)
         osb.gemm(ao, a.proj.weight, a.proj.bias, epilogue=osb.EPI_BIAS_GATE_RES, residual=xs, gate=m[:, 2],
