@@ -1,11 +1,18 @@
-// Attention for short key sets on sm_100a (tcgen05 + TMEM), one CTA per (128 query rows, head).
+// Attention for short key sets on sm_100a (tcgen05 + TMEM).
 //
-// The whole key/value set of a sequence (<= 320 keys, e.g. STDiT3 spatial S=256, temporal T=64,
-// T5 cross-attention 300) is resident in shared memory, so softmax is a single exact pass over
-// the S = Q K^T row held in TMEM - no online rescaling.  Short sequences (Lq < 128) are packed
-// G = 128/Lq per tile with a block-diagonal mask.  Per-head RMSNorm of q,k and interleaved-pair
-// RoPE are applied in fp32 while staging operands into the 128B-swizzled K-major smem tiles that
-// feed tcgen05.mma, so q/k/v are read exactly once from the projection GEMM's output.
+// One CTA (8 warps) owns one key/value set - a sequence and head (STDiT3 spatial S=256, T5
+// cross-attention 300 keys) or G = 128/Lq packed short sequences with a block-diagonal mask
+// (temporal T=64) - stages K and V^T into shared memory ONCE, then loops over up to QT 128-row query
+// tiles against it.  Because the whole key set is resident, softmax is a single exact pass over the
+// S = Q K^T row held in TMEM (no online rescaling): S via tcgen05.mma, row max / exp2 / sum by the
+// two threads that share a row (one per half of the key range), P written as bf16 into a swizzled
+// K-major tile, O = P V via tcgen05.mma, normalised in fp32 and rounded once to bf16.
+// Per-head RMSNorm of q,k and interleaved-pair RoPE are applied in fp32 while staging the operands,
+// so q/k/v are read exactly once, straight from the projection GEMM's output.
+//
+// Operand tiles are K-major: 64-wide chunks in the 128B-swizzle layout; the head-dim tail of D=72
+// (columns 64..79, zero padded) uses the no-swizzle core-matrix layout (8 rows x 16 B) so that K, Q
+// tiles cost 160 B per row instead of 256 B - this is what lets K + V^T + P + Q fit for 304 keys.
 //
 // Replaces: opensora/models/mmdit/math.py:22-36 (attention), layers.py:102-135 (QK RMSNorm) and the
 // upstream-v1.2 STDiT3 Attention / MultiHeadCrossAttention restated in SURVEY.md App. A.
@@ -13,10 +20,8 @@
 
 namespace osb {
 
-constexpr int kAttnThreads = 128;
-constexpr int kMaxKeys = 320;        // padded keys per tile
-constexpr int kSCols = 320;          // TMEM columns reserved for S
-constexpr int kChunkRowBytes = 128;  // one swizzle row = 64 bf16
+constexpr int kAttnThreads = 256;
+constexpr int kMaxKeys = 320;  // padded keys per tile
 
 struct AttnParams {
   const __nv_bfloat16* q; const __nv_bfloat16* k; const __nv_bfloat16* v; __nv_bfloat16* out;
@@ -25,118 +30,148 @@ struct AttnParams {
   int64_t q_bs, q_ss, q_ts, k_bs, k_ss, k_ts;
   int32_t Lq, Lk;
   const int32_t* kv_lens;
-  int32_t H;
   const __nv_bfloat16* qw; const __nv_bfloat16* kw;
   float eps;
   const float* cos; const float* sin;
-  float scale_log2;   // softmax_scale * log2(e)
-  int32_t G;          // sequences packed per tile
-  int32_t tiles_per_seq;
-  int32_t NK, NKP;    // keys per tile (G*Lk) and padded to 16
+  float scale_log2;      // softmax_scale * log2(e)
+  int32_t G;             // sequences packed per tile (1 when Lq >= 128)
+  int32_t tiles_per_seq; // q-tiles per sequence (G == 1)
+  int32_t QT;            // q-tiles handled per CTA (G == 1)
+  int32_t groups_per_seq;
+  int32_t NK, NKP;       // keys per CTA (G*Lk) and padded to 16
+  int32_t tmem_cols;     // 256 or 512
+  int32_t o_col;         // TMEM column of the O accumulator
+  // shared memory carve-up (bytes from the 1024-aligned base)
+  int32_t off_qt, off_k, off_kt, off_vt, off_p, off_misc;
 };
 
 template <int D>
 struct AttnCfg {
-  static constexpr int DP = (D + 15) / 16 * 16;          // padded head dim (MMA K of QK^T, N of PV)
-  static constexpr int KC = (DP + 63) / 64;              // 64-wide K chunks of Q / K tiles
-  static constexpr int Q_CHUNK = 128 * kChunkRowBytes;   // 16 KB
-  static constexpr int K_CHUNK = kMaxKeys * kChunkRowBytes;  // 40 KB
-  static constexpr int P_CHUNKS = kMaxKeys / 64;         // 5
-  static constexpr int QK_BYTES = KC * (Q_CHUNK + K_CHUNK);
-  static constexpr int P_BYTES = P_CHUNKS * Q_CHUNK;
-  static constexpr int R1_BYTES = QK_BYTES > P_BYTES ? QK_BYTES : P_BYTES;  // P overlays Q,K
-  static constexpr int VT_CHUNK = DP * kChunkRowBytes;
-  static constexpr int VT_BYTES = P_CHUNKS * VT_CHUNK;
-  static constexpr int SMEM_BYTES = R1_BYTES + VT_BYTES + 64 + 1024;
-  static_assert(kSCols + DP <= 512, "S and O must fit TMEM");
+  static constexpr int DP = (D + 15) / 16 * 16;   // padded head dim (MMA K of QK^T, N of PV)
+  static constexpr int MAIN = D / 64;             // full 64-wide swizzled chunks of the Q / K tiles
+  static constexpr int TAIL = DP - MAIN * 64;     // 0 or 16: head-dim tail in the no-swizzle layout
+  static constexpr int U = D / 8;                 // 16-byte units per head row
+  static constexpr int UP = DP / 8;
+  static constexpr int U0 = (U + 1) / 2;          // units handled by the first thread of a row pair
+  static_assert(TAIL == 0 || TAIL == 16, "head_dim tail must be one MMA K step");
+  static_assert(D % 8 == 0, "head_dim must be a multiple of 8");
 };
 
 // byte offset of 16-byte unit `u` (0..7) of row `r` inside a [rows x 64] bf16 SW128 K-major chunk
 __device__ __forceinline__ uint32_t sw128_off(int r, int u) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((u ^ (r & 7)) << 4));
 }
-
-// load one head row (D bf16), optional RMSNorm (fp32 stats, weight) and interleaved-pair RoPE
-template <int D>
-__device__ __forceinline__ void load_head_row(const __nv_bfloat16* src, const __nv_bfloat16* w,
-                                              float eps, const float* cosr, const float* sinr,
-                                              float (&x)[D]) {
-#pragma unroll
-  for (int u = 0; u < D / 8; ++u) {
-    const uint4 t = __ldg(reinterpret_cast<const uint4*>(src) + u);
-    const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = unpack_bf16x2(tw[e]);
-      x[u * 8 + 2 * e] = f.x;
-      x[u * 8 + 2 * e + 1] = f.y;
-    }
-  }
-  if (w != nullptr) {
-    float ss = 0.f;
-#pragma unroll
-    for (int d = 0; d < D; ++d) ss += x[d] * x[d];
-    const float r = rsqrtf(ss * (1.0f / D) + eps);
-#pragma unroll
-    for (int u = 0; u < D / 8; ++u) {
-      const uint4 t = __ldg(reinterpret_cast<const uint4*>(w) + u);
-      const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = unpack_bf16x2(tw[e]);
-        x[u * 8 + 2 * e] *= r * f.x;
-        x[u * 8 + 2 * e + 1] *= r * f.y;
-      }
-    }
-  }
-  if (cosr != nullptr) {
-#pragma unroll
-    for (int i = 0; i < D / 2; ++i) {
-      const float c = __ldg(cosr + i), s = __ldg(sinr + i);
-      const float a = x[2 * i], b = x[2 * i + 1];
-      x[2 * i] = a * c - b * s;
-      x[2 * i + 1] = b * c + a * s;
-    }
-  }
+// byte offset of unit `u` (0..1) of row `r` inside a [rows x 16] bf16 no-swizzle K-major tile:
+// core matrices of 8 rows x 16 B; K-adjacent core matrices 128 B apart (LBO), 8-row groups 256 B (SBO)
+__device__ __forceinline__ uint32_t tail_off(int r, int u) {
+  return (uint32_t)((r >> 3) * 256 + u * 128 + (r & 7) * 16);
+}
+__device__ __forceinline__ uint64_t make_noswz_kmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(128 >> 4) << 16;  // LBO: next core matrix along K
+  d |= static_cast<uint64_t>(256 >> 4) << 32;  // SBO: next 8-row group
+  d |= static_cast<uint64_t>(1) << 46;         // descriptor version (sm_100)
+  return d;                                    // layout type 0 = SWIZZLE_NONE
 }
 
-// store a row of D floats (padded with zeros to DP) as bf16 into K-major SW128 chunks
-template <int D, int DP>
-__device__ __forceinline__ void store_row_kmajor(uint8_t* base, int chunk_bytes, int r, const float (&x)[D]) {
+__device__ __forceinline__ void unpack8(const uint4& t, float* x) {
+  const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-  for (int u = 0; u < DP / 8; ++u) {
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = unpack_bf16x2(tw[e]);
+    x[2 * e] = f.x;
+    x[2 * e + 1] = f.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* x) {
+  uint4 o;
+  o.x = pack_bf16x2(x[0], x[1]);
+  o.y = pack_bf16x2(x[2], x[3]);
+  o.z = pack_bf16x2(x[4], x[5]);
+  o.w = pack_bf16x2(x[6], x[7]);
+  return o;
+}
+
+// Units [UB, UE) of one head row, given as raw bf16x8 registers: optional RMSNorm scale r*w and RoPE in
+// fp32 -> bf16 -> K-major operand tile (main chunks swizzled, tail no-swizzle); units >= U are zero pad.
+template <int D, int UB, int UE>
+__device__ __forceinline__ void finish_and_store_units(const uint4* raw, float r, const __nv_bfloat16* w,
+                                                       const float* cosr, const float* sinr, uint8_t* main_base,
+                                                       int main_chunk_bytes, uint8_t* tail_base, int row) {
+  using Cfg = AttnCfg<D>;
+#pragma unroll
+  for (int u = UB; u < UE; ++u) {
     uint4 o;
-    if (u * 8 < D) {
-      o.x = pack_bf16x2(x[u * 8 + 0], x[u * 8 + 1]);
-      o.y = pack_bf16x2(x[u * 8 + 2], x[u * 8 + 3]);
-      o.z = pack_bf16x2(x[u * 8 + 4], x[u * 8 + 5]);
-      o.w = pack_bf16x2(x[u * 8 + 6], x[u * 8 + 7]);
+    if (u < Cfg::U) {
+      o = raw[u - UB];
+      if (w != nullptr || cosr != nullptr) {
+        float xu[8];
+        unpack8(o, xu);
+        if (w != nullptr) {
+          float wf[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(w) + u), wf);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) xu[e] *= r * wf[e];
+        }
+        if (cosr != nullptr) {
+          const float4 c4 = __ldg(reinterpret_cast<const float4*>(cosr) + u);
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(sinr) + u);
+          const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float a = xu[2 * i], b = xu[2 * i + 1];
+            xu[2 * i] = a * cc[i] - b * ss[i];
+            xu[2 * i + 1] = b * cc[i] + a * ss[i];
+          }
+        }
+        o = pack8(xu);
+      }
     } else {
       o = make_uint4(0, 0, 0, 0);
     }
-    *reinterpret_cast<uint4*>(base + (u >> 3) * chunk_bytes + sw128_off(r, u & 7)) = o;
+    if (u < Cfg::MAIN * 8)
+      *reinterpret_cast<uint4*>(main_base + (u >> 3) * main_chunk_bytes + sw128_off(row, u & 7)) = o;
+    else
+      *reinterpret_cast<uint4*>(tail_base + tail_off(row, u - Cfg::MAIN * 8)) = o;
   }
 }
 
-template <int D>
-__global__ void __launch_bounds__(kAttnThreads, 1) attn_short_kernel(const AttnParams p) {
-  using Cfg = AttnCfg<D>;
-  constexpr int DP = Cfg::DP;
-  static_assert(D % 8 == 0, "head_dim must be a multiple of 8");
+__device__ __forceinline__ float sumsq8(const uint4& t) {
+  float x[8];
+  unpack8(t, x);
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s += x[e] * x[e];
+  return s;
+}
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sQ = smem;                                   // KC chunks of [128 x 64]
-  uint8_t* sK = smem + Cfg::KC * Cfg::Q_CHUNK;          // KC chunks of [320 x 64]
-  uint8_t* sP = smem;                                   // overlays Q,K after S is complete
-  uint8_t* sVt = smem + Cfg::R1_BYTES;                  // 5 chunks of [DP x 64]  (V transposed)
-  const uint32_t bar_s = smem_u32(smem + Cfg::R1_BYTES + Cfg::VT_BYTES);
+template <int D>
+__global__ void __launch_bounds__(kAttnThreads, (D <= 72) ? 2 : 1) attn_short_kernel(const AttnParams p) {
+  using Cfg = AttnCfg<D>;
+  constexpr int DP = Cfg::DP, U = Cfg::U, UP = Cfg::UP, U0 = Cfg::U0;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];  // 1024-byte alignment: SWIZZLE_128B atoms
+  uint8_t* smem = smem_raw;
+  uint8_t* sQ = smem;                  // MAIN chunks of [128 x 64]
+  uint8_t* sQt = smem + p.off_qt;      // [128 x 16] tail
+  uint8_t* sK = smem + p.off_k;        // MAIN chunks of [NKP x 64]
+  uint8_t* sKt = smem + p.off_kt;      // [NKP x 16] tail
+  uint8_t* sVt = smem + p.off_vt;      // ceil(NKP/64) chunks of [DP x 64]   (V transposed)
+  uint8_t* sP = smem + p.off_p;        // ceil(NKP/64) chunks of [128 x 64]
+  float* xch = reinterpret_cast<float*>(smem + p.off_misc);          // [2][128] pair exchange (ss / max)
+  float* xsum = xch + 256;                                           // [2][128] partial row sums
+  const uint32_t bar_s = smem_u32(smem + p.off_misc + 2048);
   const uint32_t bar_o = bar_s + 8;
   const uint32_t tmem_slot = bar_s + 16;
+  const int k_chunk_bytes = p.NKP * 128;
+  const int vt_chunk_bytes = DP * 128;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const int tile = blockIdx.x;
+  const int r = tid & 127;      // query row inside the tile
+  const int part = tid >> 7;    // 0/1: which member of the row pair this thread is
+  const int unit = blockIdx.x;
   const int h = blockIdx.y;
 
   if (warp == 0) {
@@ -146,43 +181,22 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_short_kernel(const AttnP
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc<1>(tmem_slot, 512);
+    tmem_alloc<1>(tmem_slot, (uint32_t)p.tmem_cols);
   }
 
-  // ---- which sequences / rows does this tile cover -------------------------------------
+  // ---- which sequences / q-tiles does this CTA cover --------------------------------------
   int64_t seq0;
-  int tok0;
-  if (p.G > 1) { seq0 = (int64_t)tile * p.G; tok0 = 0; }
-  else { seq0 = tile / p.tiles_per_seq; tok0 = (tile % p.tiles_per_seq) * 128; }
-
-  // query row of this thread
-  const int r = tid;
-  const int g = (p.G > 1) ? r / p.Lq : 0;
-  const int qtok = (p.G > 1) ? r % p.Lq : tok0 + r;
-  const int64_t qseq = seq0 + g;
-  const bool q_valid = (g < p.G) && (qseq < p.num_seqs) && (qtok < p.Lq);
-  int64_t q_row = 0;
-  if (q_valid) {
-    const int64_t b = qseq / p.seqs_per_batch, j = qseq % p.seqs_per_batch;
-    q_row = b * p.q_bs + j * p.q_ss + (int64_t)qtok * p.q_ts;
+  int qt_begin, qt_end;
+  if (p.G > 1) { seq0 = (int64_t)unit * p.G; qt_begin = 0; qt_end = 1; }
+  else {
+    seq0 = unit / p.groups_per_seq;
+    qt_begin = (unit % p.groups_per_seq) * p.QT;
+    qt_end = qt_begin + p.QT < p.tiles_per_seq ? qt_begin + p.QT : p.tiles_per_seq;
   }
 
-  // ---- stage Q ---------------------------------------------------------------------------
-  {
-    float x[D];
-    if (q_valid) {
-      load_head_row<D>(p.q + q_row * p.q_ld + (int64_t)h * D, p.qw, p.eps,
-                       p.cos ? p.cos + (int64_t)qtok * (D / 2) : nullptr,
-                       p.sin ? p.sin + (int64_t)qtok * (D / 2) : nullptr, x);
-    } else {
-#pragma unroll
-      for (int d = 0; d < D; ++d) x[d] = 0.f;
-    }
-    store_row_kmajor<D, DP>(sQ, Cfg::Q_CHUNK, r, x);
-  }
-  // ---- stage K and V^T -------------------------------------------------------------------
+  // ---- stage K and V^T once -----------------------------------------------------------------
   for (int slot = tid; slot < p.NKP; slot += kAttnThreads) {
-    const int kg = slot / p.Lk, ktok = slot % p.Lk;
+    const int kg = slot / p.Lk, ktok = slot - kg * p.Lk;
     const int64_t kseq = seq0 + kg;
     const bool k_valid = (slot < p.NK) && (kseq < p.num_seqs);
     int64_t k_row = 0;
@@ -190,167 +204,265 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_short_kernel(const AttnP
       const int64_t b = kseq / p.seqs_per_batch, j = kseq % p.seqs_per_batch;
       k_row = b * p.k_bs + j * p.k_ss + (int64_t)ktok * p.k_ts;
     }
-    float x[D];
-    if (k_valid) {
-      load_head_row<D>(p.k + k_row * p.k_ld + (int64_t)h * D, p.kw, p.eps,
-                       p.cos ? p.cos + (int64_t)ktok * (D / 2) : nullptr,
-                       p.sin ? p.sin + (int64_t)ktok * (D / 2) : nullptr, x);
+    uint4 tk[UP], tv[U];
+    if (k_valid) {  // issue every load of the slot before touching any of them
+      const uint4* ks = reinterpret_cast<const uint4*>(p.k + k_row * p.k_ld + (int64_t)h * D);
+      const uint4* vs = reinterpret_cast<const uint4*>(p.v + k_row * p.v_ld + (int64_t)h * D);
+#pragma unroll
+      for (int u = 0; u < U; ++u) tk[u] = __ldg(ks + u);
+#pragma unroll
+      for (int u = 0; u < U; ++u) tv[u] = __ldg(vs + u);
     } else {
 #pragma unroll
-      for (int d = 0; d < D; ++d) x[d] = 0.f;
+      for (int u = 0; u < U; ++u) { tk[u] = make_uint4(0, 0, 0, 0); tv[u] = make_uint4(0, 0, 0, 0); }
     }
-    store_row_kmajor<D, DP>(sK, Cfg::K_CHUNK, slot, x);
-
-    if (k_valid) {
-      load_head_row<D>(p.v + k_row * p.v_ld + (int64_t)h * D, nullptr, 0.f, nullptr, nullptr, x);
-    }  // else x is already zero
-    uint8_t* vt = sVt + (slot >> 6) * Cfg::VT_CHUNK;
-    const int kk = slot & 63;
+    float rk = 1.f;
+    if (p.kw != nullptr) {
+      float ss = 0.f;
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      *reinterpret_cast<__nv_bfloat16*>(vt + sw128_off(d, kk >> 3) + (kk & 7) * 2) = __float2bfloat16_rn(x[d]);
+      for (int u = 0; u < U; ++u) ss += sumsq8(tk[u]);
+      rk = rsqrtf(ss * (1.0f / D) + p.eps);
+    }
+    finish_and_store_units<D, 0, UP>(tk, rk, p.kw, p.cos ? p.cos + (int64_t)ktok * (D / 2) : nullptr,
+                                     p.sin ? p.sin + (int64_t)ktok * (D / 2) : nullptr, sK, k_chunk_bytes, sKt, slot);
+    // V^T: raw bf16 halves go straight to their transposed position (no fp32 round trip)
+    uint8_t* vt = sVt + (slot >> 6) * vt_chunk_bytes + (slot & 7) * 2;
+    const int ku = (slot & 63) >> 3;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t tw[4] = {tv[u].x, tv[u].y, tv[u].z, tv[u].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        *reinterpret_cast<uint16_t*>(vt + sw128_off(u * 8 + 2 * e, ku)) = (uint16_t)(tw[e] & 0xffffu);
+        *reinterpret_cast<uint16_t*>(vt + sw128_off(u * 8 + 2 * e + 1, ku)) = (uint16_t)(tw[e] >> 16);
+      }
     }
   }
 
-  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's TMEM lane quarter
 
-  // ---- S = Q K^T -------------------------------------------------------------------------
-  if (tid == 0) {
-    for (int n0 = 0; n0 < p.NKP; n0 += 256) {
-      const int n = (p.NKP - n0) < 256 ? (p.NKP - n0) : 256;
-      const uint32_t idesc = make_idesc_bf16_f32(128, n);
-      int step = 0;
+  // key chunks (32 wide) of the S row handled by this member of the row pair
+  const int n32 = (p.NKP + 31) >> 5;
+  const int c_begin = part == 0 ? 0 : (n32 + 1) / 2;
+  const int c_end = part == 0 ? (n32 + 1) / 2 : n32;
+
+  for (int qt = qt_begin; qt < qt_end; ++qt) {
+    const uint32_t par = (uint32_t)(qt - qt_begin) & 1u;
+    // ---- query row of this thread pair ---------------------------------------------------------
+    const int g = (p.G > 1) ? r / p.Lq : 0;
+    const int qtok = (p.G > 1) ? r - g * p.Lq : qt * 128 + r;
+    const int64_t qseq = seq0 + g;
+    const bool q_valid = (g < p.G) && (qseq < p.num_seqs) && (qtok < p.Lq);
+    int64_t q_row = 0;
+    if (q_valid) {
+      const int64_t b = qseq / p.seqs_per_batch, j = qseq % p.seqs_per_batch;
+      q_row = b * p.q_bs + j * p.q_ss + (int64_t)qtok * p.q_ts;
+    }
+    // ---- stage Q: the pair splits the row's units [0,U0) / [U0,UP) ------------------------------
+    {
+      const int ub = part == 0 ? 0 : U0;
+      const int ue = part == 0 ? U0 : U;
+      uint4 t[U0];
+      float ss = 0.f;
 #pragma unroll
-      for (int kc = 0; kc < Cfg::KC; ++kc) {
+      for (int i = 0; i < U0; ++i) t[i] = make_uint4(0, 0, 0, 0);
+      if (q_valid) {
+        const uint4* qs = reinterpret_cast<const uint4*>(p.q + q_row * p.q_ld + (int64_t)h * D);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          if (kc * 64 + ks * 16 >= DP) break;
-          const uint64_t da = make_sw128_kmajor_desc(smem_u32(sQ) + kc * Cfg::Q_CHUNK + ks * 32);
-          const uint64_t db = make_sw128_kmajor_desc(smem_u32(sK) + kc * Cfg::K_CHUNK + n0 * kChunkRowBytes + ks * 32);
-          umma_bf16<1>(tmem_base + n0, da, db, idesc, step > 0 ? 1u : 0u);
-          ++step;
+        for (int i = 0; i < U0; ++i)
+          if (ub + i < ue) t[i] = __ldg(qs + ub + i);
+      }
+      float rq = 1.f;
+      if (p.qw != nullptr) {
+#pragma unroll
+        for (int i = 0; i < U0; ++i) ss += sumsq8(t[i]);
+        xch[part * 128 + r] = ss;
+        __syncthreads();
+        rq = rsqrtf((xch[r] + xch[128 + r]) * (1.0f / D) + p.eps);
+      }
+      const float* cq = p.cos ? p.cos + (int64_t)qtok * (D / 2) : nullptr;
+      const float* sq = p.sin ? p.sin + (int64_t)qtok * (D / 2) : nullptr;
+      if (part == 0) finish_and_store_units<D, 0, U0>(t, rq, p.qw, cq, sq, sQ, 128 * 128, sQt, r);
+      else finish_and_store_units<D, U0, UP>(t, rq, p.qw, cq, sq, sQ, 128 * 128, sQt, r);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // ---- S = Q K^T ----------------------------------------------------------------------------
+    if (tid == 0) {
+      for (int n0 = 0; n0 < p.NKP; n0 += 256) {
+        const int n = (p.NKP - n0) < 256 ? (p.NKP - n0) : 256;
+        const uint32_t idesc = make_idesc_bf16_f32(128, n);
+        uint32_t acc = 0;
+#pragma unroll
+        for (int kc = 0; kc < Cfg::MAIN; ++kc) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t da = make_sw128_kmajor_desc(smem_u32(sQ) + kc * (128 * 128) + ks * 32);
+            const uint64_t db = make_sw128_kmajor_desc(smem_u32(sK) + kc * k_chunk_bytes + n0 * 128 + ks * 32);
+            umma_bf16<1>(tmem_base + n0, da, db, idesc, acc);
+            acc = 1;
+          }
+        }
+        if (Cfg::TAIL) {
+          const uint64_t da = make_noswz_kmajor_desc(smem_u32(sQt));
+          const uint64_t db = make_noswz_kmajor_desc(smem_u32(sKt) + (n0 >> 3) * 256);
+          umma_bf16<1>(tmem_base + n0, da, db, idesc, acc);
         }
       }
+      umma_commit<1>(bar_s);
     }
-    umma_commit<1>(bar_s);
-  }
-  mbar_wait(bar_s, 0);
-  tc_fence_after();
-
-  // ---- exact softmax over the row held in TMEM lane `r` ----------------------------------
-  int key_lo = 0, key_hi = 0;
-  if (q_valid) {
-    const int len = p.kv_lens ? p.kv_lens[qseq] : p.Lk;
-    key_lo = g * p.Lk;
-    key_hi = key_lo + (len < p.Lk ? len : p.Lk);
-  }
-  const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-  float mx = -INFINITY;
-  for (int c0 = 0; c0 < p.NKP; c0 += 32) {
-    uint32_t v[32];
-    tmem_ld_32x32b_x32(t_row + c0, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int key = c0 + j;
-      const float s = __uint_as_float(v[j]);
-      if (key >= key_lo && key < key_hi) mx = fmaxf(mx, s);
-    }
-  }
-  const float mscaled = (mx == -INFINITY) ? 0.f : mx * p.scale_log2;
-  float sum = 0.f;
-  for (int c0 = 0; c0 < p.NKP; c0 += 32) {
-    uint32_t v[32];
-    tmem_ld_32x32b_x32(t_row + c0, v);
-    tmem_ld_wait();
-    float pr[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int key = c0 + j;
-      const float s = __uint_as_float(v[j]);
-      const float e = exp2f(s * p.scale_log2 - mscaled);
-      pr[j] = (key >= key_lo && key < key_hi) ? e : 0.f;
-      sum += pr[j];
-    }
-#pragma unroll
-    for (int u4 = 0; u4 < 4; ++u4) {
-      const int u = (c0 >> 3) + u4;  // 16-byte unit index along keys
-      uint4 o;
-      o.x = pack_bf16x2(pr[u4 * 8 + 0], pr[u4 * 8 + 1]);
-      o.y = pack_bf16x2(pr[u4 * 8 + 2], pr[u4 * 8 + 3]);
-      o.z = pack_bf16x2(pr[u4 * 8 + 4], pr[u4 * 8 + 5]);
-      o.w = pack_bf16x2(pr[u4 * 8 + 6], pr[u4 * 8 + 7]);
-      *reinterpret_cast<uint4*>(sP + (u >> 3) * Cfg::Q_CHUNK + sw128_off(r, u & 7)) = o;
-    }
-  }
-  const float inv = sum > 0.f ? 1.0f / sum : 0.f;
-
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-
-  // ---- O = P V ---------------------------------------------------------------------------
-  if (tid == 0) {
-    const uint32_t idesc = make_idesc_bf16_f32(128, DP);
-    const int steps = p.NKP / 16;
-    for (int s = 0; s < steps; ++s) {
-      const int c = s >> 2, ks = s & 3;
-      const uint64_t da = make_sw128_kmajor_desc(smem_u32(sP) + c * Cfg::Q_CHUNK + ks * 32);
-      const uint64_t db = make_sw128_kmajor_desc(smem_u32(sVt) + c * Cfg::VT_CHUNK + ks * 32);
-      umma_bf16<1>(tmem_base + kSCols, da, db, idesc, s > 0 ? 1u : 0u);
-    }
-    umma_commit<1>(bar_o);
-  }
-  mbar_wait(bar_o, 0);
-  tc_fence_after();
-
-  // ---- epilogue: normalise, round once to bf16, store -------------------------------------
-  __nv_bfloat16* orow = p.out + q_row * p.out_ld + (int64_t)h * D;
-#pragma unroll 1
-  for (int c0 = 0; c0 < D; c0 += 8) {
-    uint32_t v[8];
-    tmem_ld_32x32b_x8(t_row + kSCols + c0, v);
-    tmem_ld_wait();
-    if (q_valid) {
-      uint4 o;
-      o.x = pack_bf16x2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
-      o.y = pack_bf16x2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
-      o.z = pack_bf16x2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
-      o.w = pack_bf16x2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
-      *reinterpret_cast<uint4*>(orow + c0) = o;
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
+    mbar_wait(bar_s, par);
     tc_fence_after();
-    tmem_dealloc<1>(tmem_base, 512);
+
+    // ---- exact softmax: each member of the pair owns half of the key chunks ----------------------
+    int key_lo = 0, key_hi = 0;
+    if (q_valid) {
+      const int len = p.kv_lens ? p.kv_lens[qseq] : p.Lk;
+      key_lo = g * p.Lk;
+      key_hi = key_lo + (len < p.Lk ? len : p.Lk);
+    }
+    // tcgen05.ld is warp-collective: skip decisions use the union of the warp's key ranges
+    const int w_lo = __reduce_min_sync(0xffffffffu, q_valid ? key_lo : 0x7fffffff);
+    const int w_hi = __reduce_max_sync(0xffffffffu, q_valid ? key_hi : 0);
+    float mx = -INFINITY;
+    for (int c = c_begin; c < c_end; ++c) {
+      const int c0 = c * 32;
+      if (c0 >= w_hi || c0 + 32 <= w_lo) continue;
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(t_row + c0, v);
+      tmem_ld_wait();
+      if (c0 >= key_lo && c0 + 32 <= key_hi) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j >= key_lo && c0 + j < key_hi) mx = fmaxf(mx, __uint_as_float(v[j]));
+      }
+    }
+    xch[part * 128 + r] = mx;
+    __syncthreads();
+    mx = fmaxf(xch[r], xch[128 + r]);
+    const float mscaled = (mx == -INFINITY) ? 0.f : mx * p.scale_log2;
+    float sum = 0.f;
+    for (int c = c_begin; c < c_end; ++c) {
+      const int c0 = c * 32;
+      float pr[32];
+      if (c0 >= w_hi || c0 + 32 <= w_lo) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pr[j] = 0.f;
+      } else {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + c0, v);
+        tmem_ld_wait();
+        if (c0 >= key_lo && c0 + 32 <= key_hi) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            pr[j] = exp2f(__uint_as_float(v[j]) * p.scale_log2 - mscaled);
+            sum += pr[j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float e = exp2f(__uint_as_float(v[j]) * p.scale_log2 - mscaled);
+            pr[j] = (c0 + j >= key_lo && c0 + j < key_hi) ? e : 0.f;
+            sum += pr[j];
+          }
+        }
+      }
+#pragma unroll
+      for (int u4 = 0; u4 < 4; ++u4) {
+        const int u = (c0 >> 3) + u4;  // 16-byte unit index along keys
+        *reinterpret_cast<uint4*>(sP + (u >> 3) * (128 * 128) + sw128_off(r, u & 7)) = pack8(pr + u4 * 8);
+      }
+    }
+    xsum[part * 128 + r] = sum;
+
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // ---- O = P V ---------------------------------------------------------------------------------
+    if (tid == 0) {
+      const uint32_t idesc = make_idesc_bf16_f32(128, DP);
+      const int steps = p.NKP / 16;
+      for (int s = 0; s < steps; ++s) {
+        const int c = s >> 2, ks = s & 3;
+        const uint64_t da = make_sw128_kmajor_desc(smem_u32(sP) + c * (128 * 128) + ks * 32);
+        const uint64_t db = make_sw128_kmajor_desc(smem_u32(sVt) + c * vt_chunk_bytes + ks * 32);
+        umma_bf16<1>(tmem_base + p.o_col, da, db, idesc, s > 0 ? 1u : 0u);
+      }
+      umma_commit<1>(bar_o);
+    }
+    const float tot = xsum[r] + xsum[128 + r];
+    const float inv = tot > 0.f ? 1.0f / tot : 0.f;
+    mbar_wait(bar_o, par);
+    tc_fence_after();
+
+    // ---- epilogue: normalise, round once to bf16, store (the pair splits the head columns) ----------
+    __nv_bfloat16* orow = p.out + q_row * p.out_ld + (int64_t)h * D;
+    const int ub = part == 0 ? 0 : U0, ue = part == 0 ? U0 : U;
+#pragma unroll 1
+    for (int u = ub; u < ue; ++u) {
+      uint32_t v[8];
+      tmem_ld_32x32b_x8(t_row + p.o_col + u * 8, v);
+      tmem_ld_wait();
+      if (q_valid) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[e]) * inv;
+        *reinterpret_cast<uint4*>(orow + u * 8) = pack8(o);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // S, O, sQ, sP and the exchange buffers are reused by the next q-tile
+    tc_fence_after();
   }
+
+  if (warp == 0) tmem_dealloc<1>(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 template <int D>
-static int attn_launch(const AttnParams& p, int tiles, cudaStream_t stream) {
-  dim3 grid((unsigned)tiles, (unsigned)p.H);
-  attn_short_kernel<D><<<grid, kAttnThreads, AttnCfg<D>::SMEM_BYTES, stream>>>(p);
+static int attn_launch(AttnParams& p, int64_t units, int H, cudaStream_t stream) {
+  using Cfg = AttnCfg<D>;
+  // shared memory carve-up (all tile bases 1024-byte aligned for the 128B swizzle)
+  auto up1k = [](int x) { return (x + 1023) / 1024 * 1024; };
+  const int nkc = (p.NKP + 63) / 64;
+  int off = Cfg::MAIN * 128 * 128;                 // sQ main
+  p.off_qt = off; off += up1k(Cfg::TAIL ? 128 * 32 : 0);
+  p.off_k = off; off += up1k(Cfg::MAIN * p.NKP * 128);
+  p.off_kt = off; off += up1k(Cfg::TAIL ? p.NKP * 32 : 0);
+  p.off_vt = off; off += up1k(nkc * Cfg::DP * 128);
+  p.off_p = off; off += nkc * 128 * 128;
+  p.off_misc = off; off += 2048 + 64;
+  const int smem = off;
+  const int s_cols = (p.NKP + 31) / 32 * 32;
+  p.o_col = s_cols;
+  p.tmem_cols = (s_cols + Cfg::DP <= 256) ? 256 : 512;
+  if (s_cols + Cfg::DP > 512 || smem > 227 * 1024) {
+    set_error("osb_attn_short: %d keys x head_dim %d need %d B smem / %d TMEM columns", p.NKP, D, smem, s_cols + Cfg::DP);
+    return OSB_ERR_UNSUPPORTED;
+  }
+  dim3 grid((unsigned)units, (unsigned)H);
+  attn_short_kernel<D><<<grid, kAttnThreads, smem, stream>>>(p);
   OSB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OSB_OK;
 }
 
 int attn_init() {
-  OSB_CHECK_CUDA(cudaFuncSetAttribute(attn_short_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      AttnCfg<64>::SMEM_BYTES));
-  OSB_CHECK_CUDA(cudaFuncSetAttribute(attn_short_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      AttnCfg<72>::SMEM_BYTES));
-  OSB_CHECK_CUDA(cudaFuncSetAttribute(attn_short_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      AttnCfg<128>::SMEM_BYTES));
+  OSB_CHECK_CUDA(cudaFuncSetAttribute(attn_short_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  OSB_CHECK_CUDA(cudaFuncSetAttribute(attn_short_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  OSB_CHECK_CUDA(cudaFuncSetAttribute(attn_short_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   return OSB_OK;
 }
 
@@ -373,6 +485,8 @@ extern "C" int osb_attn_short(const osb_attn_short_args* a, void* stream) {
               "osb_attn_short: tensors must be 16-byte aligned");
   OSB_REQUIRE((a->q_norm_w == nullptr) == (a->k_norm_w == nullptr), "osb_attn_short: q/k norm weights must come together");
   OSB_REQUIRE((a->rope_cos == nullptr) == (a->rope_sin == nullptr), "osb_attn_short: rope cos/sin must come together");
+  OSB_REQUIRE(a->rope_cos == nullptr || ((reinterpret_cast<uintptr_t>(a->rope_cos) | reinterpret_cast<uintptr_t>(a->rope_sin)) & 15) == 0,
+              "osb_attn_short: rope tables must be 16-byte aligned");
 
   AttnParams p;
   p.q = static_cast<const __nv_bfloat16*>(a->q);
@@ -383,34 +497,38 @@ extern "C" int osb_attn_short(const osb_attn_short_args* a, void* stream) {
   p.num_seqs = a->num_seqs; p.seqs_per_batch = a->seqs_per_batch;
   p.q_bs = a->q_batch_stride; p.q_ss = a->q_seq_stride; p.q_ts = a->q_tok_stride;
   p.k_bs = a->k_batch_stride; p.k_ss = a->k_seq_stride; p.k_ts = a->k_tok_stride;
-  p.Lq = a->Lq; p.Lk = a->Lk; p.kv_lens = a->kv_lens; p.H = a->num_heads;
+  p.Lq = a->Lq; p.Lk = a->Lk; p.kv_lens = a->kv_lens;
   p.qw = static_cast<const __nv_bfloat16*>(a->q_norm_w);
   p.kw = static_cast<const __nv_bfloat16*>(a->k_norm_w);
   p.eps = a->norm_eps;
   p.cos = a->rope_cos; p.sin = a->rope_sin;
   p.scale_log2 = a->softmax_scale * 1.4426950408889634f;
-  int64_t tiles;
+  int64_t units;
   if (a->Lq >= 128) {
     p.G = 1;
     p.tiles_per_seq = (a->Lq + 127) / 128;
-    tiles = a->num_seqs * p.tiles_per_seq;
+    // q-tiles per CTA: amortise the K/V staging, but keep >= ~2 CTAs per SM in the grid
+    int qt = p.tiles_per_seq < 8 ? p.tiles_per_seq : 8;
+    while (qt > 1 && a->num_seqs * ((p.tiles_per_seq + qt - 1) / qt) * a->num_heads < 2 * sm_count()) --qt;
+    p.QT = qt;
+    p.groups_per_seq = (p.tiles_per_seq + qt - 1) / qt;
+    units = a->num_seqs * p.groups_per_seq;
   } else {
     p.G = 128 / a->Lq;
+    // packing more sequences than the key budget allows would overflow the S tile: shrink G
+    while (p.G > 1 && (int64_t)p.G * a->Lk > kMaxKeys) --p.G;
     p.tiles_per_seq = 1;
-    tiles = (a->num_seqs + p.G - 1) / p.G;
-  }
-  // packing more sequences than the key budget allows would overflow the S tile: shrink G
-  while (p.G > 1 && (int64_t)p.G * a->Lk > kMaxKeys) {
-    --p.G;
-    tiles = (a->num_seqs + p.G - 1) / p.G;
+    p.QT = 1;
+    p.groups_per_seq = 1;
+    units = (a->num_seqs + p.G - 1) / p.G;
   }
   p.NK = p.G * a->Lk;
   OSB_REQUIRE(p.NK <= kMaxKeys, "osb_attn_short: %d keys per tile exceed the %d-key budget (use the streaming kernel)",
               p.NK, kMaxKeys);
   p.NKP = (p.NK + 15) / 16 * 16;
-  OSB_REQUIRE(tiles <= 0x7fffffff && a->num_heads <= 65535, "osb_attn_short: grid too large");
+  OSB_REQUIRE(units <= 0x7fffffff && a->num_heads <= 65535, "osb_attn_short: grid too large");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (D == 64) return attn_launch<64>(p, (int)tiles, s);
-  if (D == 72) return attn_launch<72>(p, (int)tiles, s);
-  return attn_launch<128>(p, (int)tiles, s);
+  if (D == 64) return attn_launch<64>(p, units, a->num_heads, s);
+  if (D == 72) return attn_launch<72>(p, units, a->num_heads, s);
+  return attn_launch<128>(p, units, a->num_heads, s);
 }

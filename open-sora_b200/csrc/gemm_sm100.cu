@@ -16,57 +16,68 @@ namespace osb {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
-constexpr int kNumThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
-constexpr int kStagePitch = 68;                      // floats per staged row: 64 columns + 4 pad (bank spread)
-constexpr int kEpiStageBytes = 4 * 32 * kStagePitch * 4;  // one [32 x 64] fp32 tile per epilogue warp
-constexpr int kSmemBudget = 224 * 1024 - kEpiStageBytes;
+constexpr int kEpiWarps = 8;                          // two warps per TMEM lane quarter, 32 columns each
+constexpr int kFirstEpiWarp = 3;                      // warp 0 TMA(A,W), warp 1 MMA, warp 2 TMA(residual)
+constexpr int kNumThreads = (kFirstEpiWarp + kEpiWarps) * 32;
+constexpr int kStagePitch = 36;                       // floats per staged row: 32 columns + 4 pad (bank spread)
+constexpr int kEpiStageBytes = kEpiWarps * 32 * kStagePitch * 4;  // one [32 x 32] fp32 tile per epilogue warp
+constexpr int kResChunkBytes = kBlockM * 64 * 2;      // residual ring slot: [128 rows x 64 cols] bf16, SW128
+constexpr int kBarBytes = 256;
+constexpr int kSmemTotal = 227 * 1024;
 
 struct GemmEpilogueParams {
   const __nv_bfloat16* bias;
   __nv_bfloat16* D;
-  const __nv_bfloat16* R;
   const float* gate;
   const int32_t* mod_index;
   int64_t M, N, K;
-  int64_t ldd, ldr;
+  int64_t ldd;
   int64_t group_rows;
   int64_t gate_stride;
   int32_t epilogue;
 };
 
-template <int BLOCK_N, int kCta>
+template <int BLOCK_N, int kCta, bool kRes>
 struct GemmCfg {
   static constexpr int LOAD_N = BLOCK_N / kCta;
   static constexpr int A_BYTES = kBlockM * kBlockK * 2;
   static constexpr int B_BYTES = LOAD_N * kBlockK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (kSmemBudget / STAGE_BYTES) > 8 ? 8 : (kSmemBudget / STAGE_BYTES);
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + kEpiStageBytes + 1024;  // +1024 alignment slack
+  static constexpr int RES_STAGES = kRes ? (BLOCK_N <= 128 ? 4 : 3) : 0;
+  static constexpr int RES_BYTES = RES_STAGES * kResChunkBytes;
+  static constexpr int FIXED_BYTES = RES_BYTES + kBarBytes + kEpiStageBytes + 1024;  // +1024 alignment slack
+  static constexpr int STAGES_RAW = (kSmemTotal - FIXED_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
   static constexpr uint32_t TMEM_COLS = 512;
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
   static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
   static_assert(B_BYTES % 1024 == 0, "W tile must keep 1024-byte swizzle-atom alignment");
   static_assert(BLOCK_N % 64 == 0, "epilogue works in 64-column chunks");
-  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  static_assert(2 * STAGES + 4 + 2 * 4 + 1 <= kBarBytes / 8, "barrier area");
 };
 
-template <int BLOCK_N, int kCta>
+template <int BLOCK_N, int kCta, bool kRes>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                 const GemmEpilogueParams p) {
-  using Cfg = GemmCfg<BLOCK_N, kCta>;
+                 const __grid_constant__ CUtensorMap tmap_r, const GemmEpilogueParams p) {
+  using Cfg = GemmCfg<BLOCK_N, kCta, kRes>;
   constexpr int kStages = Cfg::STAGES;
+  constexpr int kResStages = Cfg::RES_STAGES;
 
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles (the offset is identical in both CTAs of a pair)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages * Cfg::STAGE_BYTES;
+  const uint32_t res_base = smem_base + kStages * Cfg::STAGE_BYTES;            // residual ring (1024-aligned)
+  const uint32_t bar_base = res_base + Cfg::RES_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
   auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
-  const uint32_t stage_base = bar_base + Cfg::BAR_BYTES;  // epilogue staging tiles (16-byte aligned)
+  auto res_full_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 4 + s); };
+  auto res_empty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 8 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 12);
+  const uint32_t stage_base = bar_base + kBarBytes;  // epilogue staging tiles (16-byte aligned)
   auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
   auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
 
@@ -86,6 +97,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_w);
+    if constexpr (kRes) tma_prefetch_desc(&tmap_r);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -95,7 +107,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(tmem_full_bar(s), 1);
-        mbar_init(tmem_empty_bar(s), 4 * kCta);  // one lane per epilogue warp, from every CTA of the pair
+        mbar_init(tmem_empty_bar(s), kEpiWarps * kCta);  // one lane per epilogue warp, from every CTA of the pair
+      }
+      for (int s = 0; s < kResStages; ++s) {
+        mbar_init(res_full_bar(s), 1);
+        mbar_init(res_empty_bar(s), kEpiWarps);
       }
       fence_barrier_init();
     }
@@ -110,7 +126,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (A and W tiles) =====================
     if (lane == 0) {
       uint32_t leader_full[kStages];
       if constexpr (kCta == 2) {
@@ -169,15 +185,42 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
+  } else if (warp == 2) {
+    // ===================== TMA producer (residual chunks) =====================
+    // Streams the residual operand R through a ring of [128 x 64] chunks in exactly the order the
+    // epilogue consumes them, a few chunks ahead, so the epilogue never waits on an HBM round trip.
+    if constexpr (kRes) {
+      if (lane == 0) {
+        int rs = 0;
+        uint32_t rphase = 0;
+        for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+          const int64_t m_blk = tile / num_n_blocks, n_blk = tile % num_n_blocks;
+          const int32_t r_row = (int32_t)(m_blk * tile_m + cta_rank * kBlockM);
+          for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {
+            const int64_t n0 = n_blk * BLOCK_N + c0;
+            if (n0 >= p.N) break;
+            mbar_wait(res_empty_bar(rs), rphase ^ 1);
+            mbar_expect_tx(res_full_bar(rs), kResChunkBytes);
+            tma_load_2d(&tmap_r, res_full_bar(rs), res_base + rs * kResChunkBytes, (int32_t)n0, r_row);
+            if (++rs == kResStages) { rs = 0; rphase ^= 1; }
+          }
+        }
+      }
+    }
   } else {
     // ===================== epilogue warps =====================
-    // TMEM -> registers (thread = accumulator row) -> per-warp fp32 staging tile in smem -> re-read
-    // with a row-contiguous mapping so that residual loads and output stores are coalesced
-    // (4 rows x 128 B per warp instruction) instead of 32 scattered rows.
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float* stage_w = reinterpret_cast<float*>(smem_raw + (stage_base - smem_u32(smem_raw))) + q * (32 * kStagePitch);
+    // TMEM -> registers (thread = accumulator row) -> per-warp fp32 staging tile in smem -> re-read with
+    // a row-contiguous mapping so output stores are coalesced (8 rows x 64 B per warp instruction);
+    // the residual arrives through the TMA ring above (swizzled smem, conflict-free reads).
+    const int e = warp - kFirstEpiWarp;
+    const int q = warp & 3;        // TMEM lane quarter this warp may access
+    const int half = e >> 2;       // which 32-column half of each 64-column chunk
+    float* stage_w = reinterpret_cast<float*>(smem_raw + (stage_base - smem_u32(smem_raw))) + e * (32 * kStagePitch);
+    const uint8_t* res_ring = smem_raw + (res_base - smem_u32(smem_raw));
     int as = 0;
     uint32_t aphase = 0;
+    int rs = 0;
+    uint32_t rphase = 0;
     const uint32_t group_rows32 = (uint32_t)(p.group_rows > 0xffffffffll ? 0xffffffffu : p.group_rows);
     for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int64_t m_blk = tile / num_n_blocks, n_blk = tile % num_n_blocks;
@@ -187,10 +230,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {
-        uint32_t v[64];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + c0);
-        tmem_ld_32x32b_x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-        tmem_ld_32x32b_x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + c0 + half * 32);
+        tmem_ld_32x32b_x32(taddr, v);
         tmem_ld_wait();
         if (c0 + 64 >= BLOCK_N) {
           // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
@@ -202,36 +244,41 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
         const int64_t n0 = n_blk * BLOCK_N + c0;
-        if (row0 >= p.M || n0 >= p.N) continue;   // warp-uniform
+        if (n0 >= p.N) continue;  // CTA-uniform: such chunks are not in the residual ring either
         float4* my = reinterpret_cast<float4*>(stage_w + lane * kStagePitch);
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
+        for (int j = 0; j < 8; ++j)
           my[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        const uint8_t* res_slot = nullptr;
+        if constexpr (kRes) {
+          mbar_wait(res_full_bar(rs), rphase);
+          res_slot = res_ring + rs * kResChunkBytes;
+        }
         __syncwarp();
-#pragma unroll 2
-        for (int it = 0; it < 8; ++it) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
           const int i = it * 32 + lane;
-          const int rr = i >> 3, g8 = i & 7;
+          const int rr = i >> 2, g4 = i & 3;
           const int64_t row = row0 + rr;
-          const int64_t n = n0 + g8 * 8;
+          const int64_t n = n0 + half * 32 + g4 * 8;
           if (row < p.M && n < p.N) {
-            const float4 a0 = *reinterpret_cast<const float4*>(stage_w + rr * kStagePitch + g8 * 8);
-            const float4 a1 = *reinterpret_cast<const float4*>(stage_w + rr * kStagePitch + g8 * 8 + 4);
+            const float4 a0 = *reinterpret_cast<const float4*>(stage_w + rr * kStagePitch + g4 * 8);
+            const float4 a1 = *reinterpret_cast<const float4*>(stage_w + rr * kStagePitch + g4 * 8 + 4);
             float acc[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             if (p.bias) {
               const uint4 bu = __ldg(reinterpret_cast<const uint4*>(p.bias + n));
               const uint32_t bw[4] = {bu.x, bu.y, bu.z, bu.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = unpack_bf16x2(bw[e]);
-                acc[2 * e] += f.x;
-                acc[2 * e + 1] += f.y;
+              for (int k = 0; k < 4; ++k) {
+                const float2 f = unpack_bf16x2(bw[k]);
+                acc[2 * k] += f.x;
+                acc[2 * k + 1] += f.y;
               }
             }
             if (p.epilogue == OSB_EPI_BIAS_GELU_TANH) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) acc[e] = gelu_tanh(acc[e]);
+              for (int k = 0; k < 8; ++k) acc[k] = gelu_tanh(acc[k]);
             } else if (p.epilogue == OSB_EPI_BIAS_GATE_RES) {
               if (p.gate != nullptr) {
                 int64_t gi = (uint32_t)row / group_rows32;
@@ -242,14 +289,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 acc[0] *= g0.x; acc[1] *= g0.y; acc[2] *= g0.z; acc[3] *= g0.w;
                 acc[4] *= g1.x; acc[5] *= g1.y; acc[6] *= g1.z; acc[7] *= g1.w;
               }
-              if (p.R != nullptr) {
-                const uint4 ru = *reinterpret_cast<const uint4*>(p.R + row * p.ldr + n);
+              if constexpr (kRes) {
+                const int lr = q * 32 + rr;            // row inside the [128 x 64] residual chunk
+                const int u = half * 4 + g4;           // 16-byte unit inside the 128-byte row
+                const uint4 ru = *reinterpret_cast<const uint4*>(res_slot + (lr >> 3) * 1024 + (lr & 7) * 128 +
+                                                                 ((u ^ (lr & 7)) << 4));
                 const uint32_t rw[4] = {ru.x, ru.y, ru.z, ru.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = unpack_bf16x2(rw[e]);
-                  acc[2 * e] += f.x;
-                  acc[2 * e + 1] += f.y;
+                for (int k = 0; k < 4; ++k) {
+                  const float2 f = unpack_bf16x2(rw[k]);
+                  acc[2 * k] += f.x;
+                  acc[2 * k + 1] += f.y;
                 }
               }
             }
@@ -261,7 +311,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             *reinterpret_cast<uint4*>(p.D + row * p.ldd + n) = o;
           }
         }
-        __syncwarp();  // staging tile is reused by the next chunk
+        __syncwarp();  // staging tile (and the residual slot) are free again
+        if constexpr (kRes) {
+          if (lane == 0) mbar_arrive(res_empty_bar(rs));
+          if (++rs == kResStages) { rs = 0; rphase ^= 1; }
+        }
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -280,23 +334,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-template <int BLOCK_N, int kCta>
+template <int BLOCK_N, int kCta, bool kRes>
 static int launch_gemm(const osb_gemm_args& a, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, kCta>;
-  CUtensorMap ta, tw;
+  using Cfg = GemmCfg<BLOCK_N, kCta, kRes>;
+  CUtensorMap ta, tw, tr;
   int rc = make_tmap_2d_bf16(&ta, a.A, a.M, a.K, a.lda, kBlockM, kBlockK);
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tw, a.W, a.N, a.K, a.ldw, Cfg::LOAD_N, kBlockK);
   if (rc) return rc;
+  if (kRes) {
+    rc = make_tmap_2d_bf16(&tr, a.R, a.M, a.N, a.ldr, kBlockM, 64);
+    if (rc) return rc;
+  } else {
+    tr = ta;
+  }
 
   GemmEpilogueParams p;
   p.bias = static_cast<const __nv_bfloat16*>(a.bias);
   p.D = static_cast<__nv_bfloat16*>(a.D);
-  p.R = static_cast<const __nv_bfloat16*>(a.R);
   p.gate = a.gate;
   p.mod_index = a.mod_index;
   p.M = a.M; p.N = a.N; p.K = a.K;
-  p.ldd = a.ldd; p.ldr = a.ldr;
+  p.ldd = a.ldd;
   p.group_rows = a.group_rows > 0 ? a.group_rows : a.M;
   p.gate_stride = a.gate_stride;
   p.epilogue = a.epilogue;
@@ -318,34 +377,46 @@ static int launch_gemm(const osb_gemm_args& a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  OSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BLOCK_N, kCta>, ta, tw, p));
+  OSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BLOCK_N, kCta, kRes>, ta, tw, tr, p));
   count_launch();
   return OSB_OK;
 }
 
-template <int BLOCK_N, int kCta>
+template <int BLOCK_N, int kCta, bool kRes>
 static int init_one() {
-  OSB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BLOCK_N, kCta>,
+  OSB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BLOCK_N, kCta, kRes>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      GemmCfg<BLOCK_N, kCta>::SMEM_BYTES));
+                                      GemmCfg<BLOCK_N, kCta, kRes>::SMEM_BYTES));
+  return OSB_OK;
+}
+
+template <int BLOCK_N>
+static int init_bn() {
+  int rc = 0;
+  if ((rc = init_one<BLOCK_N, 1, false>())) return rc;
+  if ((rc = init_one<BLOCK_N, 1, true>())) return rc;
+  if ((rc = init_one<BLOCK_N, 2, false>())) return rc;
+  if ((rc = init_one<BLOCK_N, 2, true>())) return rc;
   return OSB_OK;
 }
 
 int gemm_init() {
   int rc = 0;
-  if ((rc = init_one<64, 1>())) return rc;
-  if ((rc = init_one<128, 1>())) return rc;
-  if ((rc = init_one<192, 1>())) return rc;
-  if ((rc = init_one<256, 1>())) return rc;
-  if ((rc = init_one<64, 2>())) return rc;
-  if ((rc = init_one<128, 2>())) return rc;
-  if ((rc = init_one<192, 2>())) return rc;
-  if ((rc = init_one<256, 2>())) return rc;
+  if ((rc = init_bn<64>())) return rc;
+  if ((rc = init_bn<128>())) return rc;
+  if ((rc = init_bn<192>())) return rc;
+  if ((rc = init_bn<256>())) return rc;
   return OSB_OK;
 }
 
-// pick the tile width that minimises (waves x per-tile time); ties go to the wider tile
+// Tile width: measured on B200 (profiles/r01_gemm_tune_v3.log) the 256-wide tile wins whenever the padding
+// of N to a multiple of 256 wastes <= 12 % (fixed per-tile cost ~ 100 columns' worth of MMA time); otherwise
+// take the candidate minimising (tiles per cluster) x (width + fixed cost).
 static int pick_block_n(int64_t M, int64_t N, int cta) {
+  if (N <= 64) return 64;
+  auto waste = [&](int bn) { return (double)((N + bn - 1) / bn * bn) / (double)N; };
+  if (waste(256) <= 1.12) return 256;
+  if (waste(192) <= 1.12) return 192;
   const int cands[3] = {256, 192, 128};
   const int64_t tile_m = (int64_t)kBlockM * cta;
   const int64_t clusters = sm_count() / cta;
@@ -353,11 +424,10 @@ static int pick_block_n(int64_t M, int64_t N, int cta) {
   int64_t best_cost = INT64_MAX;
   for (int bn : cands) {
     const int64_t tiles = ((M + tile_m - 1) / tile_m) * ((N + bn - 1) / bn);
-    const int64_t waves = (tiles + clusters - 1) / clusters;
-    const int64_t cost = waves * bn;
+    const int64_t per_cluster = (tiles + clusters - 1) / clusters;
+    const int64_t cost = per_cluster * (bn + 100);
     if (cost < best_cost) { best_cost = cost; best = bn; }
   }
-  if (N <= 64) best = 64;
   return best;
 }
 
@@ -389,8 +459,10 @@ extern "C" int osb_gemm_bf16(const osb_gemm_args* args, void* stream) {
   OSB_REQUIRE(cta == 1 || cta == 2, "osb_gemm_bf16: cta_group must be 0, 1 or 2");
   int bn = a.block_n ? a.block_n : pick_block_n(a.M, a.N, cta);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define OSB_GEMM_CASE(BN, CG) \
-  if (bn == BN && cta == CG) return launch_gemm<BN, CG>(a, s);
+  const bool has_res = (a.epilogue == OSB_EPI_BIAS_GATE_RES) && a.R != nullptr;
+#define OSB_GEMM_CASE(BN, CG)                                                   \
+  if (bn == BN && cta == CG)                                                    \
+    return has_res ? launch_gemm<BN, CG, true>(a, s) : launch_gemm<BN, CG, false>(a, s);
   OSB_GEMM_CASE(64, 1) OSB_GEMM_CASE(128, 1) OSB_GEMM_CASE(192, 1) OSB_GEMM_CASE(256, 1)
   OSB_GEMM_CASE(64, 2) OSB_GEMM_CASE(128, 2) OSB_GEMM_CASE(192, 2) OSB_GEMM_CASE(256, 2)
 #undef OSB_GEMM_CASE

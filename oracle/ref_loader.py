@@ -83,3 +83,98 @@ def load_mmdit():
         for k in [k for k in sys.modules if k == "opensora" or k.startswith("opensora.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def load_hunyuan_vae():
+    """Returns (blocks, vae) = the reference's `hunyuan_vae/unet_causal_3d_blocks.py` and `hunyuan_vae/vae.py`
+    executed by path, with stand-ins for the third-party `diffusers` pieces they import (absent in this image;
+    the reference pins nothing - header says "Modified from diffusers==0.29.2", unet_causal_3d_blocks.py:1):
+      * `get_activation("swish"|"silu")` -> nn.SiLU
+      * `Attention` -> a restatement of diffusers' AttnProcessor2_0 path with the ctor arguments the reference
+        uses (unet_causal_3d_blocks.py:311-325): GroupNorm -> q/k/v Linear -> SDPA(additive mask) -> out Linear
+        -> + residual -> / rescale_output_factor.  This piece is therefore NOT pinned by reference source.
+    """
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    saved = {k: v for k, v in sys.modules.items()
+             if k == "opensora" or k.startswith("opensora.") or k == "diffusers" or k.startswith("diffusers.")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        for pkg in ("opensora", "opensora.models", "opensora.models.hunyuan_vae", "opensora.models.vae",
+                    "opensora.acceleration", "diffusers", "diffusers.models", "diffusers.utils"):
+            _shell(pkg)
+        ck = types.ModuleType("opensora.acceleration.checkpoint")
+        ck.auto_grad_checkpoint = lambda m, *a, **k: m(*a, **k)
+        ck.checkpoint = lambda fn, *a, use_reentrant=True, **k: fn(*a, **k)
+        sys.modules["opensora.acceleration.checkpoint"] = ck
+
+        act = types.ModuleType("diffusers.models.activations")
+        act.get_activation = lambda name: nn.SiLU()
+        sys.modules["diffusers.models.activations"] = act
+
+        class Attention(nn.Module):
+            def __init__(self, query_dim, heads=1, dim_head=64, rescale_output_factor=1.0, eps=1e-6, norm_num_groups=32,
+                         spatial_norm_dim=None, residual_connection=True, bias=True, upcast_softmax=True,
+                         _from_deprecated_attn_block=True):
+                super().__init__()
+                inner = heads * dim_head
+                self.heads, self.rescale_output_factor, self.residual_connection = heads, rescale_output_factor, residual_connection
+                self.group_norm = nn.GroupNorm(num_channels=query_dim, num_groups=norm_num_groups, eps=eps, affine=True)
+                self.to_q = nn.Linear(query_dim, inner, bias=bias)
+                self.to_k = nn.Linear(query_dim, inner, bias=bias)
+                self.to_v = nn.Linear(query_dim, inner, bias=bias)
+                self.to_out = nn.ModuleList([nn.Linear(inner, query_dim, bias=True), nn.Dropout(0.0)])
+
+            def forward(self, hidden_states, attention_mask=None):
+                residual = hidden_states
+                B, L, C = hidden_states.shape
+                h = self.group_norm(hidden_states.transpose(1, 2)).transpose(1, 2)
+                q, k, v = self.to_q(h), self.to_k(h), self.to_v(h)
+                hd = C // self.heads
+                q, k, v = (t.view(B, L, self.heads, hd).transpose(1, 2) for t in (q, k, v))
+                m = attention_mask
+                if m is not None:
+                    m = m.view(B, 1, L, L) if m.dim() == 3 else m
+                o = F.scaled_dot_product_attention(q, k, v, attn_mask=m, dropout_p=0.0, is_causal=False)
+                o = o.transpose(1, 2).reshape(B, L, C)
+                o = self.to_out[1](self.to_out[0](o))
+                if self.residual_connection:
+                    o = o + residual
+                return o / self.rescale_output_factor
+
+        ap = types.ModuleType("diffusers.models.attention_processor")
+        ap.Attention = Attention
+        sys.modules["diffusers.models.attention_processor"] = ap
+        du = sys.modules["diffusers.utils"]
+
+        class _Log:
+            @staticmethod
+            def get_logger(name):
+                import logging
+
+                return logging.getLogger(name)
+
+        du.logging = _Log
+
+        class BaseOutput(dict):
+            pass
+
+        du.BaseOutput = BaseOutput
+        tu = types.ModuleType("diffusers.utils.torch_utils")
+        tu.randn_tensor = lambda shape, generator=None, device=None, dtype=None: torch.randn(
+            shape, generator=generator, device=device, dtype=dtype)
+        sys.modules["diffusers.utils.torch_utils"] = tu
+        base = os.path.join(REF, "opensora", "models")
+        _load("opensora.models.vae.utils", os.path.join(base, "vae", "utils.py"))
+        blocks = _load("opensora.models.hunyuan_vae.unet_causal_3d_blocks",
+                       os.path.join(base, "hunyuan_vae", "unet_causal_3d_blocks.py"))
+        vae = _load("opensora.models.hunyuan_vae.vae", os.path.join(base, "hunyuan_vae", "vae.py"))
+        return blocks, vae
+    finally:
+        for k in [k for k in sys.modules if k == "opensora" or k.startswith("opensora.") or k == "diffusers"
+                  or k.startswith("diffusers.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
