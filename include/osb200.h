@@ -113,6 +113,56 @@ typedef struct osb_attn_short_args {
  * (SURVEY.md §8a-S, Appendix A). */
 int osb_attn_short(const osb_attn_short_args* args, void* stream);
 
+/* ---- causal 3D VAE: implicit-GEMM convolution + its HBM-bound helpers ----------------------------- */
+typedef struct osb_conv3d_args {
+  const void* x_pad;    /* bf16 NDHWC [nb, tp, hp, wp, cp]: input ALREADY padded (replicate; T front only) by
+                           osb_vae_prep; in narrow mode the buffer must extend 128 bytes past its end        */
+  const void* w;        /* bf16 [cout, K] K-major.  normal: K = kt*kh*kw*cp, k = ((it*kh+ih)*kw+iw)*cp + c;
+                           narrow: K = kt*kh*64, k = (it*kh+ih)*64 + iw*cp + c (zero where iw*cp+c >= kw*cp)  */
+  const void* bias;     /* bf16 [cout] or NULL                                                                 */
+  void* y;              /* bf16 NDHWC [nb, t_out, h_out, w_out, cout]                                          */
+  const void* residual; /* bf16 like y, added in fp32 before the single rounding; or NULL                      */
+  int32_t nb, tp, hp, wp, cp;
+  int32_t t_out, h_out, w_out, cout;
+  int32_t st, sh, sw;   /* strides (1 or 2)                                                                    */
+  int32_t kt, kh, kw;   /* taps (1..3)                                                                         */
+  int32_t narrow;       /* 1: cp in {8,16}, the kw taps x cp channels form one 64-element K block             */
+  int32_t block_n;      /* 0 = library default                                                                 */
+} osb_conv3d_args;
+
+/* y = conv3d(x_pad) + bias (+ residual), fp32 accumulation in TMEM, one rounding to bf16.  Every k-block is a
+ * 5-D TMA box load of the padded NDHWC input at the tap offset (strided boxes for stride-2 convolutions), fed to
+ * the same tcgen05 main loop and epilogue as osb_gemm_bf16.
+ * Replaces: opensora/models/hunyuan_vae/unet_causal_3d_blocks.py:94-96 (CausalConv3d.forward: F.pad replicate +
+ * ChannelChunkConv3d) and opensora/models/vae/utils.py:172-190 (the cuDNN conv3d it dispatches to). */
+int osb_conv3d_ndhwc(const osb_conv3d_args* args, void* stream);
+
+/* GroupNorm statistics over an NDHWC tensor: for every (n, group) the mean and 1/sqrt(var + eps) over
+ * (C/groups) channels x T*H*W positions.  `sums` is a caller-provided fp64 scratch [nb, groups, 2] that the
+ * call zeroes, fills by atomics and finalises into mean_rstd fp32 [nb, groups, 2].
+ * Replaces the statistics half of torch.nn.GroupNorm at unet_causal_3d_blocks.py:216,218,246-250; vae.py:115,229. */
+int osb_group_stats(const void* x, int64_t nb, int64_t positions, int32_t C, int32_t groups, float eps,
+                    double* sums, float* mean_rstd, void* stream);
+
+typedef struct osb_vae_prep_args {
+  const void* x;           /* bf16 NDHWC [nb, t, h, w, c]                                                      */
+  void* y;                 /* bf16 NDHWC [nb, tp, hp, wp, cp]                                                  */
+  const float* mean_rstd;  /* [nb, groups, 2] from osb_group_stats, or NULL = no normalisation                 */
+  const void* gamma;       /* bf16 [c] GroupNorm weight (with mean_rstd)                                       */
+  const void* beta;        /* bf16 [c]                                                                         */
+  int32_t nb, t, h, w, c;
+  int32_t groups;
+  int32_t silu;            /* apply x*sigmoid(x) after the affine                                              */
+  int32_t ft, fh, fw;      /* nearest-neighbour upsample factors (1 or 2); T rule: frame 0 -> 1 frame, others x ft */
+  int32_t pad_t, pad_h, pad_w; /* replicate padding: pad_t frames in FRONT only, pad_h / pad_w on both sides    */
+  int32_t cp;              /* output channels >= c (zero filled), multiple of 8                                */
+} osb_vae_prep_args;
+
+/* One HBM pass that produces the convolution's input: GroupNorm apply + SiLU + nearest upsample (first-frame
+ * rule) + replicate padding, written channels-last.  Replaces the separate GroupNorm / SiLU / F.interpolate /
+ * F.pad passes of unet_causal_3d_blocks.py:95,136-150,246-250. */
+int osb_vae_prep(const osb_vae_prep_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

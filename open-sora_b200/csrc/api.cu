@@ -53,6 +53,38 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_
   return OSB_OK;
 }
 
+int make_tmap_5d_bf16(CUtensorMap* map, const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],
+                      const uint32_t box[5], const uint32_t elem_strides[5]) {
+  if (!g_encode) {
+    set_error("osb_init() has not been called");
+    return OSB_ERR_NOT_INIT;
+  }
+  if (reinterpret_cast<uintptr_t>(base) & 15) {
+    set_error("TMA operand must be 16-byte aligned (base %p)", base);
+    return OSB_ERR_INVALID;
+  }
+  cuuint64_t gdim[5], gstride[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < 5; ++i) { gdim[i] = dims[i]; b[i] = box[i]; es[i] = elem_strides[i]; }
+  for (int i = 0; i < 4; ++i) {
+    if (strides_bytes[i] & 15) {
+      set_error("TMA stride %d (%llu bytes) is not a multiple of 16", i, (unsigned long long)strides_bytes[i]);
+      return OSB_ERR_INVALID;
+    }
+    gstride[i] = strides_bytes[i];
+  }
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstride, b, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(5D) failed with CUresult %d (dims %llu %llu %llu %llu %llu box %u %u %u %u %u)", (int)r,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+              (unsigned long long)dims[3], (unsigned long long)dims[4], box[0], box[1], box[2], box[3], box[4]);
+    return OSB_ERR_CUDA;
+  }
+  return OSB_OK;
+}
+
 int gemm_init();   // gemm_sm100.cu
 int attn_init();   // attn_short_sm100.cu
 

@@ -507,9 +507,19 @@ extern "C" int osb_attn_short(const osb_attn_short_args* a, void* stream) {
   if (a->Lq >= 128) {
     p.G = 1;
     p.tiles_per_seq = (a->Lq + 127) / 128;
-    // q-tiles per CTA: amortise the K/V staging, but keep >= ~2 CTAs per SM in the grid
-    int qt = p.tiles_per_seq < 8 ? p.tiles_per_seq : 8;
-    while (qt > 1 && a->num_seqs * ((p.tiles_per_seq + qt - 1) / qt) * a->num_heads < 2 * sm_count()) --qt;
+    // q-tiles per CTA: amortise the K/V staging against whole waves of CTAs (1 CTA per SM at these smem sizes).
+    // cost(QT) = waves x (QT + staging), staging ~ 0.9 q-tile-equivalents per 256 keys (measured, profiles/).
+    const double staging = 0.9 * (double)a->Lk / 256.0;
+    int qt = 1;
+    double best = 1e30;
+    for (int cand = 1; cand <= p.tiles_per_seq && cand <= 64; ++cand) {
+      const int64_t groups = (p.tiles_per_seq + cand - 1) / cand;
+      const int64_t ctas = a->num_seqs * groups * a->num_heads;
+      const int64_t waves = (ctas + sm_count() - 1) / sm_count();
+      const double per_cta = (double)((p.tiles_per_seq + groups - 1) / groups) + staging;
+      const double cost = (double)waves * per_cta;
+      if (cost < best - 1e-9) { best = cost; qt = cand; }
+    }
     p.QT = qt;
     p.groups_per_seq = (p.tiles_per_seq + qt - 1) / qt;
     units = a->num_seqs * p.groups_per_seq;

@@ -43,6 +43,11 @@ int sm_count();
 int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t ld, uint32_t box_rows, uint32_t box_cols);
 
+// 5D tiled tensor map over bf16 data: dims/box/element strides innermost first, strides in BYTES for
+// dims 1..4 (multiples of 16), 128-byte swizzle (box[0] must be 64 elements), zero OOB fill.
+int make_tmap_5d_bf16(CUtensorMap* map, const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],
+                      const uint32_t box[5], const uint32_t elem_strides[5]);
+
 // ------------------------------------------------------------------------------------------
 // device side
 // ------------------------------------------------------------------------------------------
@@ -167,6 +172,24 @@ __device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap* m, uint32_t b
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
       "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// 5D tile loads (NDHWC activations of the causal-conv VAE: coordinates c, w, h, t, n)
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* m, uint32_t bar, uint32_t dst, int32_t c0,
+                                            int32_t c1, int32_t c2, int32_t c3, int32_t c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_cg2(const CUtensorMap* m, uint32_t bar_cluster, uint32_t dst,
+                                                int32_t c0, int32_t c1, int32_t c2, int32_t c3, int32_t c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 

@@ -37,6 +37,18 @@ struct GemmEpilogueParams {
   int32_t epilogue;
 };
 
+// Implicit-GEMM view of a causal 3D convolution over a (replicate-)padded NDHWC activation tensor: one
+// CTA owns a Tt x Ht x Wt box of output positions (128 rows); CTA pairs stack two boxes along H.  The K loop
+// walks (kt, kh, kw) taps x 64-channel chunks; every k-block is ONE 5-D TMA box load at the tap's offset.
+struct ConvGeom {
+  int32_t wt_log2, ht_log2;              // box: Wt = 1 << wt_log2, Ht = 1 << ht_log2, Tt = 128 / (Wt * Ht)
+  int32_t tiles_w, tiles_h, tiles_t, nb; // (pair-)tiles per dimension, batch
+  int32_t w_out, h_out, t_out;
+  int32_t sw, sh, st;                    // convolution strides
+  int32_t kw_n, kh_n;                    // taps along w, h (taps along t = k-blocks / (kw_n * kh_n * cin_chunks))
+  int32_t cin_chunks;                    // 64-wide channel chunks per tap
+};
+
 template <int BLOCK_N, int kCta, bool kRes>
 struct GemmCfg {
   static constexpr int LOAD_N = BLOCK_N / kCta;
@@ -57,10 +69,10 @@ struct GemmCfg {
   static_assert(2 * STAGES + 4 + 2 * 4 + 1 <= kBarBytes / 8, "barrier area");
 };
 
-template <int BLOCK_N, int kCta, bool kRes>
+template <int BLOCK_N, int kCta, bool kRes, bool kConv>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                 const __grid_constant__ CUtensorMap tmap_r, const GemmEpilogueParams p) {
+                 const __grid_constant__ CUtensorMap tmap_r, const GemmEpilogueParams p, const ConvGeom cg) {
   using Cfg = GemmCfg<BLOCK_N, kCta, kRes>;
   constexpr int kStages = Cfg::STAGES;
   constexpr int kResStages = Cfg::RES_STAGES;
@@ -87,7 +99,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const bool is_leader = cta_rank == 0;
 
   const int64_t tile_m = (int64_t)kBlockM * kCta;
-  const int64_t num_m_blocks = (p.M + tile_m - 1) / tile_m;
+  const int64_t num_m_blocks = kConv ? (int64_t)cg.nb * cg.tiles_t * cg.tiles_h * cg.tiles_w : (p.M + tile_m - 1) / tile_m;
+  // conv: m_blk -> (batch, t-tile, h-tile, w-tile); this CTA's box origin in OUTPUT coordinates
+  auto conv_origin = [&](int64_t m_blk, int& n_i, int& t0, int& h0, int& w0) {
+    const int tw = (int)(m_blk % cg.tiles_w);
+    const int th = (int)((m_blk / cg.tiles_w) % cg.tiles_h);
+    const int tt = (int)((m_blk / ((int64_t)cg.tiles_w * cg.tiles_h)) % cg.tiles_t);
+    n_i = (int)(m_blk / ((int64_t)cg.tiles_w * cg.tiles_h * cg.tiles_t));
+    w0 = tw << cg.wt_log2;
+    h0 = (th * kCta + (int)cta_rank) << cg.ht_log2;
+    t0 = tt * (128 >> (cg.wt_log2 + cg.ht_log2));
+  };
   const int64_t num_n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int64_t num_tiles = num_m_blocks * num_n_blocks;
   const int64_t num_k_blocks = (p.K + kBlockK - 1) / kBlockK;
@@ -139,16 +161,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int64_t m_blk = tile / num_n_blocks, n_blk = tile % num_n_blocks;
         const int32_t a_row = (int32_t)(m_blk * tile_m + cta_rank * kBlockM);
         const int32_t w_row = (int32_t)(n_blk * BLOCK_N + cta_rank * Cfg::LOAD_N);
+        int n_i = 0, t0 = 0, h0 = 0, w0 = 0;
+        if constexpr (kConv) conv_origin(m_blk, n_i, t0, h0, w0);
         for (int64_t kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const int32_t k0 = (int32_t)(kb * kBlockK);
+          int32_t ac = 0, aw = 0, ah = 0, at = 0;
+          if constexpr (kConv) {  // tap offsets in the padded input, output origin scaled by the stride
+            const int tap = (int)(kb / cg.cin_chunks);
+            ac = (int32_t)(kb - (int64_t)tap * cg.cin_chunks) * kBlockK;
+            aw = w0 * cg.sw + tap % cg.kw_n;
+            ah = h0 * cg.sh + (tap / cg.kw_n) % cg.kh_n;
+            at = t0 * cg.st + tap / (cg.kw_n * cg.kh_n);
+          }
           if constexpr (kCta == 1) {
             mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-            tma_load_2d(&tmap_a, full_bar(stage), smem_a(stage), k0, a_row);
+            if constexpr (kConv) tma_load_5d(&tmap_a, full_bar(stage), smem_a(stage), ac, aw, ah, at, n_i);
+            else tma_load_2d(&tmap_a, full_bar(stage), smem_a(stage), k0, a_row);
             tma_load_2d(&tmap_w, full_bar(stage), smem_b(stage), k0, w_row);
           } else {
             if (is_leader) mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * 2);
-            tma_load_2d_cg2(&tmap_a, leader_full[stage], smem_a(stage), k0, a_row);
+            if constexpr (kConv) tma_load_5d_cg2(&tmap_a, leader_full[stage], smem_a(stage), ac, aw, ah, at, n_i);
+            else tma_load_2d_cg2(&tmap_a, leader_full[stage], smem_a(stage), k0, a_row);
             tma_load_2d_cg2(&tmap_w, leader_full[stage], smem_b(stage), k0, w_row);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -196,12 +230,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
           const int64_t m_blk = tile / num_n_blocks, n_blk = tile % num_n_blocks;
           const int32_t r_row = (int32_t)(m_blk * tile_m + cta_rank * kBlockM);
+          int n_i = 0, t0 = 0, h0 = 0, w0 = 0;
+          if constexpr (kConv) conv_origin(m_blk, n_i, t0, h0, w0);
           for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {
             const int64_t n0 = n_blk * BLOCK_N + c0;
             if (n0 >= p.N) break;
             mbar_wait(res_empty_bar(rs), rphase ^ 1);
             mbar_expect_tx(res_full_bar(rs), kResChunkBytes);
-            tma_load_2d(&tmap_r, res_full_bar(rs), res_base + rs * kResChunkBytes, (int32_t)n0, r_row);
+            if constexpr (kConv) tma_load_5d(&tmap_r, res_full_bar(rs), res_base + rs * kResChunkBytes, (int32_t)n0, w0, h0, t0, n_i);
+            else tma_load_2d(&tmap_r, res_full_bar(rs), res_base + rs * kResChunkBytes, (int32_t)n0, r_row);
             if (++rs == kResStages) { rs = 0; rphase ^= 1; }
           }
         }
@@ -225,6 +262,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int64_t m_blk = tile / num_n_blocks, n_blk = tile % num_n_blocks;
       const int64_t row0 = m_blk * tile_m + cta_rank * kBlockM + q * 32;  // first row of this warp
+      int n_i = 0, t0 = 0, h0 = 0, w0 = 0;
+      if constexpr (kConv) conv_origin(m_blk, n_i, t0, h0, w0);
       mbar_wait(tmem_full_bar(as), aphase);
       tc_fence_after();
 
@@ -260,9 +299,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int it = 0; it < 4; ++it) {
           const int i = it * 32 + lane;
           const int rr = i >> 2, g4 = i & 3;
-          const int64_t row = row0 + rr;
+          int64_t row = row0 + rr;
+          bool row_ok = row < p.M;
+          if constexpr (kConv) {  // box-local row -> (t, h, w) output position -> flattened NDHWC row
+            const int li = q * 32 + rr;
+            const int w = w0 + (li & ((1 << cg.wt_log2) - 1));
+            const int h = h0 + ((li >> cg.wt_log2) & ((1 << cg.ht_log2) - 1));
+            const int t = t0 + (li >> (cg.wt_log2 + cg.ht_log2));
+            row_ok = w < cg.w_out && h < cg.h_out && t < cg.t_out;
+            row = (((int64_t)n_i * cg.t_out + t) * cg.h_out + h) * cg.w_out + w;
+          }
           const int64_t n = n0 + half * 32 + g4 * 8;
-          if (row < p.M && n < p.N) {
+          if (row_ok && n < p.N) {
             const float4 a0 = *reinterpret_cast<const float4*>(stage_w + rr * kStagePitch + g4 * 8);
             const float4 a1 = *reinterpret_cast<const float4*>(stage_w + rr * kStagePitch + g4 * 8 + 4);
             float acc[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
@@ -334,6 +382,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+template <int BLOCK_N, int kCta, bool kRes, bool kConv>
+static int launch_kernel(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tr, const GemmEpilogueParams& p,
+                         const ConvGeom& cg, int64_t tiles, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N, kCta, kRes>;
+  int64_t clusters = sm_count() / kCta;
+  if (tiles < clusters) clusters = tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * kCta));
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  OSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BLOCK_N, kCta, kRes, kConv>, ta, tw, tr, p, cg));
+  count_launch();
+  return OSB_OK;
+}
+
 template <int BLOCK_N, int kCta, bool kRes>
 static int launch_gemm(const osb_gemm_args& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, kCta, kRes>;
@@ -362,31 +433,20 @@ static int launch_gemm(const osb_gemm_args& a, cudaStream_t stream) {
 
   const int64_t tile_m = (int64_t)kBlockM * kCta;
   const int64_t tiles = ((a.M + tile_m - 1) / tile_m) * ((a.N + BLOCK_N - 1) / BLOCK_N);
-  int64_t clusters = sm_count() / kCta;
-  if (tiles < clusters) clusters = tiles;
-
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(clusters * kCta));
-  cfg.blockDim = dim3(kNumThreads);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCta;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  OSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BLOCK_N, kCta, kRes>, ta, tw, tr, p));
-  count_launch();
-  return OSB_OK;
+  ConvGeom cg = {};
+  return launch_kernel<BLOCK_N, kCta, kRes, false>(ta, tw, tr, p, cg, tiles, stream);
 }
 
 template <int BLOCK_N, int kCta, bool kRes>
 static int init_one() {
-  OSB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BLOCK_N, kCta, kRes>,
+  OSB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BLOCK_N, kCta, kRes, false>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       GemmCfg<BLOCK_N, kCta, kRes>::SMEM_BYTES));
+  if (kCta == 2) {  // the convolution path always pairs CTAs
+    OSB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BLOCK_N, kCta, kRes, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        GemmCfg<BLOCK_N, kCta, kRes>::SMEM_BYTES));
+  }
   return OSB_OK;
 }
 
@@ -431,6 +491,59 @@ static int pick_block_n(int64_t M, int64_t N, int cta) {
   return best;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// causal 3D convolution as implicit GEMM (NDHWC, input already replicate-padded by osb_vae_prep)
+// ------------------------------------------------------------------------------------------
+template <int BLOCK_N, bool kRes>
+static int launch_conv(const osb_conv3d_args& a, const ConvGeom& cg, const uint32_t box[5], cudaStream_t stream) {
+  constexpr int kCta = 2;
+  using Cfg = GemmCfg<BLOCK_N, kCta, kRes>;
+  CUtensorMap ta, tw, tr;
+  const uint64_t cp = a.cp;
+  int rc;
+  if (a.narrow) {
+    // overlapping windows: 64 contiguous elements starting at every w (stride Cp elements): (kw, c) folded
+    const uint64_t dims[5] = {64, (uint64_t)a.wp, (uint64_t)a.hp, (uint64_t)a.tp, (uint64_t)a.nb};
+    const uint64_t str[4] = {cp * 2, (uint64_t)a.wp * cp * 2, (uint64_t)a.hp * a.wp * cp * 2,
+                             (uint64_t)a.tp * a.hp * a.wp * cp * 2};
+    const uint32_t es[5] = {1, (uint32_t)a.sw, (uint32_t)a.sh, (uint32_t)a.st, 1};
+    rc = make_tmap_5d_bf16(&ta, a.x_pad, dims, str, box, es);
+  } else {
+    const uint64_t dims[5] = {cp, (uint64_t)a.wp, (uint64_t)a.hp, (uint64_t)a.tp, (uint64_t)a.nb};
+    const uint64_t str[4] = {cp * 2, (uint64_t)a.wp * cp * 2, (uint64_t)a.hp * a.wp * cp * 2,
+                             (uint64_t)a.tp * a.hp * a.wp * cp * 2};
+    const uint32_t es[5] = {1, (uint32_t)a.sw, (uint32_t)a.sh, (uint32_t)a.st, 1};
+    rc = make_tmap_5d_bf16(&ta, a.x_pad, dims, str, box, es);
+  }
+  if (rc) return rc;
+  const int64_t K = (int64_t)(a.narrow ? a.kt * a.kh : a.kt * a.kh * a.kw * (a.cp / 64)) * 64;
+  rc = make_tmap_2d_bf16(&tw, a.w, a.cout, K, K, Cfg::LOAD_N, kBlockK);
+  if (rc) return rc;
+  if (kRes) {
+    const uint64_t dims[5] = {(uint64_t)a.cout, (uint64_t)a.w_out, (uint64_t)a.h_out, (uint64_t)a.t_out, (uint64_t)a.nb};
+    const uint64_t c2 = (uint64_t)a.cout * 2;
+    const uint64_t str[4] = {c2, a.w_out * c2, (uint64_t)a.h_out * a.w_out * c2, (uint64_t)a.t_out * a.h_out * a.w_out * c2};
+    const uint32_t rbox[5] = {64, 1u << cg.wt_log2, 1u << cg.ht_log2, 128u >> (cg.wt_log2 + cg.ht_log2), 1};
+    const uint32_t es[5] = {1, 1, 1, 1, 1};
+    rc = make_tmap_5d_bf16(&tr, a.residual, dims, str, rbox, es);
+    if (rc) return rc;
+  } else {
+    tr = tw;
+  }
+  GemmEpilogueParams p = {};
+  p.bias = static_cast<const __nv_bfloat16*>(a.bias);
+  p.D = static_cast<__nv_bfloat16*>(a.y);
+  p.M = (int64_t)a.nb * a.t_out * a.h_out * a.w_out;
+  p.N = a.cout;
+  p.K = K;
+  p.ldd = a.cout;
+  p.group_rows = p.M;
+  p.epilogue = kRes ? OSB_EPI_BIAS_GATE_RES : OSB_EPI_BIAS;
+  const int64_t tiles = (int64_t)cg.nb * cg.tiles_t * cg.tiles_h * cg.tiles_w * ((a.cout + BLOCK_N - 1) / BLOCK_N);
+  return launch_kernel<BLOCK_N, kCta, kRes, true>(ta, tw, tr, p, cg, tiles, stream);
+}
+
 }  // namespace osb
 
 extern "C" int osb_gemm_bf16(const osb_gemm_args* args, void* stream) {
@@ -467,5 +580,62 @@ extern "C" int osb_gemm_bf16(const osb_gemm_args* args, void* stream) {
   OSB_GEMM_CASE(64, 2) OSB_GEMM_CASE(128, 2) OSB_GEMM_CASE(192, 2) OSB_GEMM_CASE(256, 2)
 #undef OSB_GEMM_CASE
   set_error("osb_gemm_bf16: unsupported block_n %d", bn);
+  return OSB_ERR_UNSUPPORTED;
+}
+
+extern "C" int osb_conv3d_ndhwc(const osb_conv3d_args* args, void* stream) {
+  using namespace osb;
+  if (!initialised()) { set_error("osb_init() has not been called"); return OSB_ERR_NOT_INIT; }
+  OSB_REQUIRE(args != nullptr, "osb_conv3d_ndhwc: null args");
+  const osb_conv3d_args& a = *args;
+  OSB_REQUIRE(a.x_pad && a.w && a.y, "osb_conv3d_ndhwc: null tensor");
+  OSB_REQUIRE(a.nb > 0 && a.t_out > 0 && a.h_out > 0 && a.w_out > 0 && a.cout > 0, "osb_conv3d_ndhwc: empty output");
+  OSB_REQUIRE(a.cout % 8 == 0, "osb_conv3d_ndhwc: Cout must be a multiple of 8 (pad the weights), got %d", a.cout);
+  OSB_REQUIRE(a.st >= 1 && a.st <= 2 && a.sh >= 1 && a.sh <= 2 && a.sw >= 1 && a.sw <= 2, "osb_conv3d_ndhwc: strides must be 1 or 2");
+  OSB_REQUIRE(a.kt >= 1 && a.kh >= 1 && a.kw >= 1 && a.kt <= 3 && a.kh <= 3 && a.kw <= 3, "osb_conv3d_ndhwc: taps must be 1..3");
+  if (a.narrow) {
+    OSB_REQUIRE((a.cp == 8 || a.cp == 16) && a.kw * a.cp <= 64,
+                "osb_conv3d_ndhwc: narrow mode needs Cp in {8,16} with kw*Cp <= 64 (Cp %d kw %d)", a.cp, a.kw);
+  } else {
+    OSB_REQUIRE(a.cp % 64 == 0, "osb_conv3d_ndhwc: Cp must be a multiple of 64 (or use narrow mode), got %d", a.cp);
+  }
+  OSB_REQUIRE((a.t_out - 1) * a.st + a.kt <= a.tp && (a.h_out - 1) * a.sh + a.kh <= a.hp && (a.w_out - 1) * a.sw + a.kw <= a.wp,
+              "osb_conv3d_ndhwc: padded input [%d,%d,%d] too small for output [%d,%d,%d]", a.tp, a.hp, a.wp, a.t_out,
+              a.h_out, a.w_out);
+  OSB_REQUIRE(((reinterpret_cast<uintptr_t>(a.x_pad) | reinterpret_cast<uintptr_t>(a.w) | reinterpret_cast<uintptr_t>(a.y) |
+                reinterpret_cast<uintptr_t>(a.bias) | reinterpret_cast<uintptr_t>(a.residual)) & 15) == 0,
+              "osb_conv3d_ndhwc: tensors must be 16-byte aligned");
+
+  // box of 128 output positions per CTA (pairs stack along H): minimise padded work, prefer wide W
+  ConvGeom cg = {};
+  double best = 1e30;
+  for (int wl = 7; wl >= 3; --wl) {
+    for (int hl = 0; wl + hl <= 7; ++hl) {
+      const int Wt = 1 << wl, Ht = 1 << hl, Tt = 128 >> (wl + hl);
+      const int64_t tw = (a.w_out + Wt - 1) / Wt, th = (a.h_out + 2 * Ht - 1) / (2 * Ht), tt = (a.t_out + Tt - 1) / Tt;
+      const double work = (double)(tw * Wt) * (double)(th * 2 * Ht) * (double)(tt * Tt);
+      if (work < best * 0.999) {
+        best = work;
+        cg.wt_log2 = wl; cg.ht_log2 = hl;
+        cg.tiles_w = (int)tw; cg.tiles_h = (int)th; cg.tiles_t = (int)tt;
+      }
+    }
+  }
+  cg.nb = a.nb;
+  cg.w_out = a.w_out; cg.h_out = a.h_out; cg.t_out = a.t_out;
+  cg.sw = a.sw; cg.sh = a.sh; cg.st = a.st;
+  cg.kw_n = a.narrow ? 1 : a.kw; cg.kh_n = a.kh;
+  cg.cin_chunks = a.narrow ? 1 : a.cp / 64;
+  const uint32_t box[5] = {64, (uint32_t)((1 << cg.wt_log2) * a.sw), (uint32_t)((1 << cg.ht_log2) * a.sh),
+                           (uint32_t)((128 >> (cg.wt_log2 + cg.ht_log2)) * a.st), 1};
+  int bn = a.block_n;
+  if (bn == 0) bn = a.cout <= 64 ? 64 : (a.cout <= 128 ? 128 : (a.cout % 256 == 0 ? 256 : (a.cout % 192 == 0 ? 192 : 256)));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool has_res = a.residual != nullptr;
+#define OSB_CONV_CASE(BN) \
+  if (bn == BN) return has_res ? launch_conv<BN, true>(a, cg, box, s) : launch_conv<BN, false>(a, cg, box, s);
+  OSB_CONV_CASE(64) OSB_CONV_CASE(128) OSB_CONV_CASE(192) OSB_CONV_CASE(256)
+#undef OSB_CONV_CASE
+  set_error("osb_conv3d_ndhwc: unsupported block_n %d", bn);
   return OSB_ERR_UNSUPPORTED;
 }

@@ -1,1 +1,1 @@
-from . import stdit  # noqa: F401  (registers STDiT3-XL/2 etc. in opensora.registry.MODELS)
+from . import hunyuan_vae, stdit  # noqa: F401  (registers "hunyuan_vae", "STDiT3-XL/2", ... in opensora.registry.MODELS)

@@ -1,0 +1,230 @@
+"""Causal 3D VAE building blocks on the osb200 kernels (channels-last NDHWC inside, bf16).
+
+Same class names, constructor meaning and state-dict keys as the reference's
+`opensora/models/hunyuan_vae/unet_causal_3d_blocks.py` (`CausalConv3d` :63-96, `UpsampleCausal3D` :98-158,
+`DownsampleCausal3D` :160-181, `ResnetBlockCausal3D` :184-259, `UNetMidBlockCausal3D` :262-355,
+`DownEncoderBlockCausal3D`, `UpDecoderBlockCausal3D`).  The nn.Modules hold parameters only; `forward` takes and
+returns **NDHWC bf16** tensors and runs on libosb200: GroupNorm statistics (`osb_group_stats`), one fused
+GN-apply + SiLU + nearest-upsample + replicate-pad pass (`osb_vae_prep`) and the implicit-GEMM convolution
+(`osb_conv3d_ndhwc`, tcgen05, residual add fused in the epilogue).  1x1x1 convolutions are plain GEMMs.
+No CPU / eager fallback."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+
+def _osb():
+    import osb200
+
+    return osb200
+
+
+class CausalConv3d(nn.Module):
+    """Parameter container + launcher.  `forward(x, norm=..., silu=..., up=..., residual=...)`: the optional
+    GroupNorm(+SiLU) and nearest upsample that PRECEDE this convolution in the reference are folded into the
+    padding pass that builds its input."""
+
+    def __init__(self, chan_in, chan_out, kernel_size=3, stride=1, dilation=1, pad_mode="replicate", **kwargs):
+        super().__init__()
+        assert pad_mode == "replicate" and dilation == 1
+        self.kernel_size = kernel_size
+        self.stride = (stride,) * 3 if isinstance(stride, int) else tuple(stride)
+        self.time_causal_padding = (kernel_size // 2,) * 4 + (kernel_size - 1, 0)
+        self.conv = nn.Conv3d(chan_in, chan_out, kernel_size, stride=self.stride, **kwargs)  # parameters only
+        self._packed = None
+
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        return super()._apply(fn, *a, **k)
+
+    def _weights(self):
+        if self._packed is None:
+            osb = _osb()
+            w, b = self.conv.weight, self.conv.bias
+            cout, cin = w.shape[:2]
+            co = (cout + 7) // 8 * 8
+            if self.kernel_size == 1:
+                wp = torch.zeros(co, cin, dtype=torch.bfloat16, device=w.device)
+                wp[:cout] = w.reshape(cout, cin)
+                narrow, cp = False, cin
+            else:
+                narrow = cin <= 16
+                cp = ((cin + 7) // 8 * 8 if cin <= 8 else 16) if narrow else (cin + 63) // 64 * 64
+                wp = osb.pack_conv_weight(w.detach(), cp, narrow, cout_pad=co)
+            bp = None
+            if b is not None:
+                bp = torch.zeros(co, dtype=torch.bfloat16, device=w.device)
+                bp[:cout] = b.detach()
+            self._packed = (wp.contiguous(), bp, narrow, cp, cout)
+        return self._packed
+
+    def forward(self, x, norm: nn.GroupNorm | None = None, silu: bool = False, up=(1, 1, 1), residual=None):
+        osb = _osb()
+        if not x.is_cuda or x.dtype != torch.bfloat16:
+            raise osb.OsbError("hunyuan_vae (osb200) runs on CUDA in bfloat16, channels-last inside; no fallback")
+        wp, bp, narrow, cp, cout = self._weights()
+        nb, T, H, W, C = x.shape
+        if self.kernel_size == 1:
+            assert norm is None and not silu and up == (1, 1, 1)
+            y = osb.gemm(x.reshape(-1, C), wp, bp, epilogue=osb.EPI_BIAS if residual is None else osb.EPI_BIAS_GATE_RES,
+                         residual=None if residual is None else residual.reshape(-1, wp.shape[0]))
+            return y.view(nb, T, H, W, wp.shape[0])
+        stats = gamma = beta = None
+        groups = 1
+        if norm is not None:
+            groups = norm.num_groups
+            stats = osb.group_stats(x, groups, norm.eps)
+            gamma, beta = norm.weight, norm.bias
+        xp = osb.vae_prep(x, stats=stats, gamma=gamma, beta=beta, groups=groups, silu=silu, up=up,
+                          pad=(self.kernel_size - 1, self.kernel_size // 2, self.kernel_size // 2), cp=cp)
+        tp, hp, wpd = xp.shape[1:4]
+        st, sh, sw = self.stride
+        k = self.kernel_size
+        out_thw = ((tp - k) // st + 1, (hp - k) // sh + 1, (wpd - k) // sw + 1)
+        y = osb.conv3d(xp, wp, bp, out_thw=out_thw, stride=self.stride, taps=(k, k, k), narrow=narrow, residual=residual)
+        return y if wp.shape[0] == cout else y[..., :cout]
+
+
+class UpsampleCausal3D(nn.Module):
+    def __init__(self, channels, out_channels=None, kernel_size=3, bias=True, upsample_factor=(2, 2, 2)):
+        super().__init__()
+        self.channels, self.out_channels = channels, out_channels or channels
+        self.upsample_factor = tuple(upsample_factor)
+        self.conv = CausalConv3d(self.channels, self.out_channels, kernel_size=kernel_size, bias=bias)
+
+    def forward(self, x):
+        return self.conv(x, up=self.upsample_factor)  # nearest upsample is address arithmetic in the padding pass
+
+
+class DownsampleCausal3D(nn.Module):
+    def __init__(self, channels, kernel_size=3, bias=True, stride=2):
+        super().__init__()
+        self.channels = self.out_channels = channels
+        self.conv = CausalConv3d(channels, channels, kernel_size=kernel_size, stride=stride, bias=bias)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class ResnetBlockCausal3D(nn.Module):
+    def __init__(self, *, in_channels, out_channels=None, dropout=0.0, groups=32, groups_out=None, pre_norm=True,
+                 eps=1e-6, non_linearity="swish", output_scale_factor=1.0, use_in_shortcut=None,
+                 conv_shortcut_bias=True, conv_3d_out_channels=None):
+        super().__init__()
+        out_channels = in_channels if out_channels is None else out_channels
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.output_scale_factor = output_scale_factor
+        assert output_scale_factor == 1.0 and dropout == 0.0
+        self.norm1 = nn.GroupNorm(groups, in_channels, eps=eps, affine=True)
+        self.conv1 = CausalConv3d(in_channels, out_channels, kernel_size=3, stride=1)
+        self.norm2 = nn.GroupNorm(groups_out or groups, out_channels, eps=eps, affine=True)
+        c3 = conv_3d_out_channels or out_channels
+        self.conv2 = CausalConv3d(out_channels, c3, kernel_size=3, stride=1)
+        self.use_in_shortcut = in_channels != c3 if use_in_shortcut is None else use_in_shortcut
+        self.conv_shortcut = CausalConv3d(in_channels, c3, kernel_size=1, stride=1, bias=conv_shortcut_bias) \
+            if self.use_in_shortcut else None
+
+    def forward(self, x):
+        h = self.conv1(x, norm=self.norm1, silu=True)
+        sc = x if self.conv_shortcut is None else self.conv_shortcut(x)
+        return self.conv2(h, norm=self.norm2, silu=True, residual=sc)  # (shortcut + h) fused in the conv epilogue
+
+
+class _MidAttention(nn.Module):
+    """State-dict twin of the diffusers `Attention` the reference instantiates at unet_causal_3d_blocks.py:311-325
+    (1 head of C dims, GroupNorm, bias, residual): group_norm, to_q, to_k, to_v, to_out.0."""
+
+    def __init__(self, channels, groups, eps):
+        super().__init__()
+        self.group_norm = nn.GroupNorm(groups, channels, eps=eps, affine=True)
+        self.to_q = nn.Linear(channels, channels)
+        self.to_k = nn.Linear(channels, channels)
+        self.to_v = nn.Linear(channels, channels)
+        self.to_out = nn.ModuleList([nn.Linear(channels, channels), nn.Dropout(0.0)])
+
+    def forward(self, x):
+        osb = _osb()
+        nb, T, H, W, C = x.shape
+        hw = H * W
+        stats = osb.group_stats(x, self.group_norm.num_groups, self.group_norm.eps)
+        h = osb.vae_prep(x, stats=stats, gamma=self.group_norm.weight, beta=self.group_norm.bias,
+                         groups=self.group_norm.num_groups, slack_bytes=0).view(nb * T * hw, C)
+        q = osb.gemm(h, self.to_q.weight, self.to_q.bias).view(nb, 1, T * hw, C)
+        k = osb.gemm(h, self.to_k.weight, self.to_k.bias).view(nb, 1, T * hw, C)
+        v = osb.gemm(h, self.to_v.weight, self.to_v.bias).view(nb, 1, T * hw, C)
+        # Frame-causal attention (prepare_causal_attention_mask, :52-60): frame f attends to frames <= f, so the
+        # mask is never materialised - one un-masked SDPA per query frame over the key prefix.  LIBRARY kernel
+        # (torch SDPA, head_dim 512): the osb200 streaming attention for D=512 is the next kernel on this row.
+        o = torch.empty_like(q)
+        for f in range(T):
+            o[:, :, f * hw:(f + 1) * hw] = torch.nn.functional.scaled_dot_product_attention(
+                q[:, :, f * hw:(f + 1) * hw], k[:, :, :(f + 1) * hw], v[:, :, :(f + 1) * hw])
+        out = osb.gemm(o.view(nb * T * hw, C), self.to_out[0].weight, self.to_out[0].bias, epilogue=osb.EPI_BIAS_GATE_RES,
+                       residual=x.reshape(nb * T * hw, C))
+        return out.view(nb, T, H, W, C)
+
+
+class UNetMidBlockCausal3D(nn.Module):
+    def __init__(self, in_channels, dropout=0.0, num_layers=1, resnet_eps=1e-6, resnet_act_fn="swish", resnet_groups=32,
+                 attn_groups=None, resnet_pre_norm=True, add_attention=True, attention_head_dim=1, output_scale_factor=1.0):
+        super().__init__()
+        self.add_attention = add_attention
+        attn_groups = attn_groups or resnet_groups
+        mk = lambda: ResnetBlockCausal3D(in_channels=in_channels, out_channels=in_channels, eps=resnet_eps,  # noqa: E731
+                                         groups=resnet_groups, output_scale_factor=output_scale_factor)
+        resnets, attentions = [mk()], []
+        for _ in range(num_layers):
+            attentions.append(_MidAttention(in_channels, attn_groups, resnet_eps) if add_attention else None)
+            resnets.append(mk())
+        self.attentions = nn.ModuleList(attentions)
+        self.resnets = nn.ModuleList(resnets)
+
+    def forward(self, x, attention_mask=None):
+        x = self.resnets[0](x)
+        for attn, resnet in zip(self.attentions, self.resnets[1:]):
+            if attn is not None:
+                x = attn(x)
+            x = resnet(x)
+        return x
+
+
+class DownEncoderBlockCausal3D(nn.Module):
+    def __init__(self, in_channels, out_channels, dropout=0.0, num_layers=1, resnet_eps=1e-6, resnet_act_fn="swish",
+                 resnet_groups=32, resnet_pre_norm=True, output_scale_factor=1.0, add_downsample=True, downsample_stride=2):
+        super().__init__()
+        self.resnets = nn.ModuleList([
+            ResnetBlockCausal3D(in_channels=in_channels if i == 0 else out_channels, out_channels=out_channels,
+                                eps=resnet_eps, groups=resnet_groups, output_scale_factor=output_scale_factor)
+            for i in range(num_layers)])
+        self.downsamplers = nn.ModuleList([DownsampleCausal3D(out_channels, stride=downsample_stride)]) if add_downsample else None
+
+    def forward(self, x):
+        for r in self.resnets:
+            x = r(x)
+        if self.downsamplers is not None:
+            for d in self.downsamplers:
+                x = d(x)
+        return x
+
+
+class UpDecoderBlockCausal3D(nn.Module):
+    def __init__(self, in_channels, out_channels, resolution_idx=None, dropout=0.0, num_layers=1, resnet_eps=1e-6,
+                 resnet_act_fn="swish", resnet_groups=32, resnet_pre_norm=True, output_scale_factor=1.0,
+                 add_upsample=True, upsample_scale_factor=(2, 2, 2)):
+        super().__init__()
+        self.resnets = nn.ModuleList([
+            ResnetBlockCausal3D(in_channels=in_channels if i == 0 else out_channels, out_channels=out_channels,
+                                eps=resnet_eps, groups=resnet_groups, output_scale_factor=output_scale_factor)
+            for i in range(num_layers)])
+        self.upsamplers = nn.ModuleList([UpsampleCausal3D(out_channels, out_channels=out_channels,
+                                                          upsample_factor=upsample_scale_factor)]) if add_upsample else None
+        self.resolution_idx = resolution_idx
+
+    def forward(self, x):
+        for r in self.resnets:
+            x = r(x)
+        if self.upsamplers is not None:
+            for u in self.upsamplers:
+                x = u(x)
+        return x

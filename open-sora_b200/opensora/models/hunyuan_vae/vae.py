@@ -1,0 +1,117 @@
+"""EncoderCausal3D / DecoderCausal3D / DiagonalGaussianDistribution with the reference's names, constructor
+arguments and state-dict keys (`opensora/models/hunyuan_vae/vae.py:40-150,153-277,280-340`), running on the
+osb200 kernels.  Encoder/decoder take and return **NDHWC bf16** (the NCDHW<->NDHWC conversion happens once at
+`AutoencoderKLCausal3D.encode/decode`)."""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from .unet_causal_3d_blocks import CausalConv3d, DownEncoderBlockCausal3D, UNetMidBlockCausal3D, UpDecoderBlockCausal3D
+
+
+def _plan(n_blocks, time_compression_ratio, spatial_compression_ratio):
+    """(down strides, up factors) per block: vae.py:66-88 and :190-212."""
+    ns, nt = int(math.log2(spatial_compression_ratio)), int(math.log2(time_compression_ratio))
+    if time_compression_ratio not in (4, 8):
+        raise ValueError(f"Unsupported time_compression_ratio: {time_compression_ratio}.")
+    out = []
+    for i in range(n_blocks):
+        final = i == n_blocks - 1
+        sp = i < ns
+        tm = ((i >= n_blocks - 1 - nt) and not final) if time_compression_ratio == 4 else sp
+        out.append((2 if tm else 1, 2 if sp else 1, 2 if sp else 1) if (sp or tm) else None)
+    return out
+
+
+class EncoderCausal3D(nn.Module):
+    def __init__(self, in_channels=3, out_channels=3, block_out_channels=(64,), layers_per_block=2, norm_num_groups=32,
+                 act_fn="silu", double_z=True, mid_block_add_attention=True, time_compression_ratio=4,
+                 spatial_compression_ratio=8, dropout=0.0):
+        super().__init__()
+        self.layers_per_block = layers_per_block
+        self.conv_in = CausalConv3d(in_channels, block_out_channels[0], kernel_size=3, stride=1)
+        self.down_blocks = nn.ModuleList([])
+        plan = _plan(len(block_out_channels), time_compression_ratio, spatial_compression_ratio)
+        oc = block_out_channels[0]
+        for i, ch in enumerate(block_out_channels):
+            ic, oc = oc, ch
+            self.down_blocks.append(DownEncoderBlockCausal3D(
+                num_layers=layers_per_block, in_channels=ic, out_channels=oc, add_downsample=plan[i] is not None,
+                downsample_stride=plan[i] or 1, resnet_eps=1e-6, resnet_groups=norm_num_groups))
+        self.mid_block = UNetMidBlockCausal3D(in_channels=block_out_channels[-1], resnet_eps=1e-6, output_scale_factor=1,
+                                              attention_head_dim=block_out_channels[-1], resnet_groups=norm_num_groups,
+                                              add_attention=mid_block_add_attention)
+        self.conv_norm_out = nn.GroupNorm(num_channels=block_out_channels[-1], num_groups=norm_num_groups, eps=1e-6)
+        self.conv_act = nn.SiLU()
+        self.conv_out = CausalConv3d(block_out_channels[-1], 2 * out_channels if double_z else out_channels, kernel_size=3)
+
+    def forward(self, sample):  # NDHWC bf16 (channels padded to a multiple of 8)
+        x = self.conv_in(sample)
+        for blk in self.down_blocks:
+            x = blk(x)
+        x = self.mid_block(x)
+        return self.conv_out(x, norm=self.conv_norm_out, silu=True)
+
+
+class DecoderCausal3D(nn.Module):
+    def __init__(self, in_channels=3, out_channels=3, block_out_channels=(64,), layers_per_block=2, norm_num_groups=32,
+                 act_fn="silu", mid_block_add_attention=True, time_compression_ratio=4, spatial_compression_ratio=8,
+                 dropout=0.0):
+        super().__init__()
+        self.layers_per_block = layers_per_block
+        self.conv_in = CausalConv3d(in_channels, block_out_channels[-1], kernel_size=3, stride=1)
+        self.mid_block = UNetMidBlockCausal3D(in_channels=block_out_channels[-1], resnet_eps=1e-6, output_scale_factor=1,
+                                              attention_head_dim=block_out_channels[-1], resnet_groups=norm_num_groups,
+                                              add_attention=mid_block_add_attention)
+        self.up_blocks = nn.ModuleList([])
+        rev = list(reversed(block_out_channels))
+        plan = _plan(len(block_out_channels), time_compression_ratio, spatial_compression_ratio)
+        oc = rev[0]
+        for i, ch in enumerate(rev):
+            pc, oc = oc, ch
+            self.up_blocks.append(UpDecoderBlockCausal3D(
+                num_layers=layers_per_block + 1, in_channels=pc, out_channels=oc, add_upsample=plan[i] is not None,
+                upsample_scale_factor=plan[i] or (1, 1, 1), resnet_eps=1e-6, resnet_groups=norm_num_groups))
+        self.conv_norm_out = nn.GroupNorm(num_channels=block_out_channels[0], num_groups=norm_num_groups, eps=1e-6)
+        self.conv_act = nn.SiLU()
+        self.conv_out = CausalConv3d(block_out_channels[0], out_channels, kernel_size=3)
+
+    def forward(self, sample):  # NDHWC bf16 latent
+        x = self.conv_in(sample)
+        x = self.mid_block(x)
+        for blk in self.up_blocks:
+            x = blk(x)
+        return self.conv_out(x, norm=self.conv_norm_out, silu=True)
+
+
+class DiagonalGaussianDistribution:
+    """vae.py:280-340 (NCDHW parameters; trivial elementwise work, kept in torch)."""
+
+    def __init__(self, parameters: torch.Tensor, deterministic: bool = False):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.deterministic = deterministic
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+        if self.deterministic:
+            self.var = self.std = torch.zeros_like(self.mean)
+
+    def sample(self, generator=None) -> torch.Tensor:
+        noise = torch.randn(self.mean.shape, generator=generator, device=self.parameters.device, dtype=self.parameters.dtype)
+        return self.mean + self.std * noise
+
+    def kl(self, other=None) -> torch.Tensor:
+        if self.deterministic:
+            return torch.Tensor([0.0])
+        red = list(range(1, self.mean.ndim))
+        if other is None:
+            return 0.5 * torch.sum(torch.pow(self.mean, 2) + self.var - 1.0 - self.logvar, dim=red)
+        return 0.5 * torch.sum(torch.pow(self.mean - other.mean, 2) / other.var + self.var / other.var - 1.0
+                               - self.logvar + other.logvar, dim=red)
+
+    def mode(self) -> torch.Tensor:
+        return self.mean

@@ -21,6 +21,9 @@ EXPORTS = (
     "osb_ln_modulate",
     "osb_gemm_bf16",
     "osb_attn_short",
+    "osb_conv3d_ndhwc",
+    "osb_group_stats",
+    "osb_vae_prep",
 )
 
 EPI_BIAS, EPI_BIAS_GELU_TANH, EPI_BIAS_GATE_RES = 0, 1, 2
@@ -49,6 +52,10 @@ def _load() -> C.CDLL:
     ]
     lib.osb_gemm_bf16.argtypes = [C.c_void_p, C.c_void_p]
     lib.osb_attn_short.argtypes = [C.c_void_p, C.c_void_p]
+    lib.osb_conv3d_ndhwc.argtypes = [C.c_void_p, C.c_void_p]
+    lib.osb_vae_prep.argtypes = [C.c_void_p, C.c_void_p]
+    lib.osb_group_stats.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]
     return lib
 
 
@@ -121,6 +128,28 @@ class AttnShortArgs(C.Structure):
         ("norm_eps", C.c_float),
         ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
         ("softmax_scale", C.c_float),
+    ]
+
+
+class Conv3dArgs(C.Structure):
+    _fields_ = [
+        ("x_pad", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("y", C.c_void_p), ("residual", C.c_void_p),
+        ("nb", C.c_int32), ("tp", C.c_int32), ("hp", C.c_int32), ("wp", C.c_int32), ("cp", C.c_int32),
+        ("t_out", C.c_int32), ("h_out", C.c_int32), ("w_out", C.c_int32), ("cout", C.c_int32),
+        ("st", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
+        ("kt", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
+        ("narrow", C.c_int32), ("block_n", C.c_int32),
+    ]
+
+
+class VaePrepArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("y", C.c_void_p), ("mean_rstd", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("nb", C.c_int32), ("t", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
+        ("groups", C.c_int32), ("silu", C.c_int32),
+        ("ft", C.c_int32), ("fh", C.c_int32), ("fw", C.c_int32),
+        ("pad_t", C.c_int32), ("pad_h", C.c_int32), ("pad_w", C.c_int32),
+        ("cp", C.c_int32),
     ]
 
 
@@ -256,3 +285,96 @@ def attn_short(q, k, v, out, *, num_seqs: int, seqs_per_batch: int, q_strides, k
     with _Timed("attn_short", 4.0 * num_seqs * Lq * Lk * num_heads * head_dim):  # QK^T + PV FLOPs
         _check(_lib.osb_attn_short(C.byref(a), _stream()), "osb_attn_short")
     return out
+
+
+# ---- causal 3D VAE ops (NDHWC) -------------------------------------------------------------------------
+def group_stats(x, groups: int, eps: float = 1e-6):
+    """GroupNorm statistics of x bf16 [nb, T, H, W, C] (channels last) -> fp32 [nb, groups, 2] = (mean, rstd)."""
+    import torch
+
+    _need(x, torch.bfloat16, "x")
+    assert x.dim() == 5 and x.is_contiguous()
+    nb, Cc = x.shape[0], x.shape[-1]
+    pos = x.shape[1] * x.shape[2] * x.shape[3]
+    sums = torch.empty(nb, groups, 2, dtype=torch.float64, device=x.device)
+    out = torch.empty(nb, groups, 2, dtype=torch.float32, device=x.device)
+    with _Timed("group_stats", 2.0 * x.numel()):  # algorithmic bytes: one read
+        _check(_lib.osb_group_stats(_ptr(x), nb, pos, Cc, groups, eps, _ptr(sums), _ptr(out), _stream()), "osb_group_stats")
+    return out
+
+
+def vae_prep(x, *, stats=None, gamma=None, beta=None, groups: int = 32, silu: bool = False, up=(1, 1, 1),
+             pad=(0, 0, 0), cp: int | None = None, slack_bytes: int = 128):
+    """[GroupNorm-apply + SiLU] + nearest upsample + replicate pad of x bf16 [nb,T,H,W,C] -> padded bf16
+    [nb,Tp,Hp,Wp,cp] (one pass).  pad = (front frames, rows each side, cols each side)."""
+    import torch
+
+    _need(x, torch.bfloat16, "x"); _need(stats, torch.float32, "stats")
+    _need(gamma, torch.bfloat16, "gamma"); _need(beta, torch.bfloat16, "beta")
+    assert x.dim() == 5 and x.is_contiguous()
+    nb, T, H, W, Cc = x.shape
+    cp = cp or Cc
+    tu = T if up[0] == 1 else 1 + up[0] * (T - 1)
+    tp, hp, wp = tu + pad[0], H * up[1] + 2 * pad[1], W * up[2] + 2 * pad[2]
+    n = nb * tp * hp * wp * cp
+    buf = torch.empty(n + slack_bytes // 2, dtype=torch.bfloat16, device=x.device)  # slack: narrow-mode windows
+    if slack_bytes:
+        buf[n:].zero_()
+    y = buf[:n].view(nb, tp, hp, wp, cp)
+    a = VaePrepArgs()
+    a.x, a.y = x.data_ptr(), y.data_ptr()
+    a.mean_rstd = stats.data_ptr() if stats is not None else None
+    a.gamma = gamma.data_ptr() if gamma is not None else None
+    a.beta = beta.data_ptr() if beta is not None else None
+    a.nb, a.t, a.h, a.w, a.c = nb, T, H, W, Cc
+    a.groups, a.silu = groups, int(silu)
+    a.ft, a.fh, a.fw = up
+    a.pad_t, a.pad_h, a.pad_w = pad
+    a.cp = cp
+    with _Timed("vae_prep", 2.0 * (x.numel() + n)):
+        _check(_lib.osb_vae_prep(C.byref(a), _stream()), "osb_vae_prep")
+    return y
+
+
+def conv3d(x_pad, w_packed, bias, *, out_thw, stride=(1, 1, 1), taps=(3, 3, 3), narrow: bool = False, residual=None,
+           block_n: int = 0):
+    """y = conv3d(x_pad) + bias (+ residual): x_pad bf16 [nb,Tp,Hp,Wp,Cp] (already padded), w_packed bf16 [Cout, K]
+    (see pack_conv_weight), y bf16 [nb, T_out, H_out, W_out, Cout]."""
+    import torch
+
+    _need(x_pad, torch.bfloat16, "x_pad"); _need(w_packed, torch.bfloat16, "w_packed"); _need(bias, torch.bfloat16, "bias")
+    _need(residual, torch.bfloat16, "residual")
+    nb, tp, hp, wp, cp = x_pad.shape
+    cout = w_packed.shape[0]
+    y = torch.empty(nb, *out_thw, cout, dtype=torch.bfloat16, device=x_pad.device)
+    a = Conv3dArgs()
+    a.x_pad, a.w, a.y = x_pad.data_ptr(), w_packed.data_ptr(), y.data_ptr()
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.residual = residual.data_ptr() if residual is not None else None
+    a.nb, a.tp, a.hp, a.wp, a.cp = nb, tp, hp, wp, cp
+    a.t_out, a.h_out, a.w_out = out_thw
+    a.cout = cout
+    a.st, a.sh, a.sw = stride
+    a.kt, a.kh, a.kw = taps
+    a.narrow, a.block_n = int(narrow), block_n
+    with _Timed("conv3d", 2.0 * y.numel() * w_packed.shape[1]):  # MACs incl. K padding (algorithmic count is the caller's)
+        _check(_lib.osb_conv3d_ndhwc(C.byref(a), _stream()), "osb_conv3d_ndhwc")
+    return y
+
+
+def pack_conv_weight(w, cp: int, narrow: bool, cout_pad: int | None = None):
+    """torch Conv3d weight [Cout, Cin, kt, kh, kw] -> bf16 [Cout_p, K] K-major in the order the kernel walks K
+    (include/osb200.h osb_conv3d_args.w).  Done once at load time."""
+    import torch
+
+    cout, cin, kt, kh, kw = w.shape
+    co = cout_pad or cout
+    if narrow:
+        out = torch.zeros(co, kt * kh, 64, dtype=w.dtype, device=w.device)
+        blk = torch.zeros(cout, kt * kh, kw, cp, dtype=w.dtype, device=w.device)
+        blk[..., :cin] = w.permute(0, 2, 3, 4, 1).reshape(cout, kt * kh, kw, cin)
+        out[:cout, :, : kw * cp] = blk.reshape(cout, kt * kh, kw * cp)
+        return out.reshape(co, kt * kh * 64).to(torch.bfloat16).contiguous()
+    out = torch.zeros(co, kt, kh, kw, cp, dtype=w.dtype, device=w.device)
+    out[:cout, ..., :cin] = w.permute(0, 2, 3, 4, 1)
+    return out.reshape(co, kt * kh * kw * cp).to(torch.bfloat16).contiguous()

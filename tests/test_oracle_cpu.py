@@ -145,3 +145,50 @@ def test_algorithmic_flop_model():
     import bench
 
     assert abs(bench.algorithmic_flops() / 1e12 - 36.13) < 0.01
+
+
+# ---- causal 3D VAE oracle pinned by reference-executed goldens --------------------------------------
+from oracle import vae_oracle as V  # noqa: E402
+
+GV = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(HERE, "golden", "vae_blocks.npz")).items()}
+VTOL = dict(rtol=1e-4, atol=1e-4)
+
+
+def _wv(prefix):
+    return {k[len(prefix) + 1:]: v for k, v in GV.items() if k.startswith(prefix + ".")}
+
+
+@pytest.mark.parametrize("tag,stride", [("s111", (1, 1, 1)), ("s122", (1, 2, 2)), ("s222", (2, 2, 2))])
+def test_causal_conv3d_matches_reference(tag, stride):
+    y = V.causal_conv3d(GV["conv_x"], GV[f"conv_{tag}.w"], GV[f"conv_{tag}.b"], stride)
+    torch.testing.assert_close(y, GV[f"conv_{tag}.y"], **VTOL)
+
+
+def test_causal_conv3d_k1_and_causality():
+    torch.testing.assert_close(V.causal_conv3d(GV["conv_x"], GV["conv_k1.w"], GV["conv_k1.b"]), GV["conv_k1.y"], **VTOL)
+    x = GV["conv_x"].clone()
+    y0 = V.causal_conv3d(x, GV["conv_s111.w"], GV["conv_s111.b"])
+    x[:, :, -1] += 1.0  # perturbing the last frame must leave all earlier output frames bit-identical
+    y1 = V.causal_conv3d(x, GV["conv_s111.w"], GV["conv_s111.b"])
+    assert torch.equal(y0[:, :, :-1], y1[:, :, :-1]) and not torch.equal(y0[:, :, -1], y1[:, :, -1])
+
+
+@pytest.mark.parametrize("tag,f", [("u222", (2, 2, 2)), ("u122", (1, 2, 2))])
+def test_upsample_matches_reference(tag, f):
+    y = V.causal_conv3d(V.upsample_causal3d(GV["conv_x"], f), GV[f"up_{tag}.w"], GV[f"up_{tag}.b"])
+    torch.testing.assert_close(y, GV[f"up_{tag}.y"], **VTOL)
+
+
+@pytest.mark.parametrize("tag", ["same", "wide"])
+def test_resnet_block_matches_reference(tag):
+    torch.testing.assert_close(V.resnet_block(_wv(f"res_{tag}"), "", GV["res_x"], groups=4), GV[f"res_{tag}.y"], **VTOL)
+
+
+def test_mid_block_and_encoder_decoder_match_reference():
+    torch.testing.assert_close(V.mid_block(_wv("mid"), "", GV["res_x"], groups=4), GV["mid.y"], **VTOL)
+    down, up = V.stage_plan(4, 4, 8)
+    assert down == [(1, 2, 2), (2, 2, 2), (2, 2, 2), None] and up == [(1, 2, 2), (2, 2, 2), (2, 2, 2), None]
+    z = V.encoder(_wv("enc"), GV["enc_x"], groups=4, strides=down)
+    torch.testing.assert_close(z, GV["enc_y"], rtol=1e-3, atol=1e-3)
+    y = V.decoder(_wv("dec"), GV["enc_y"][:, :4], groups=4, factors=up)
+    torch.testing.assert_close(y, GV["dec_y"], rtol=1e-3, atol=1e-3)
