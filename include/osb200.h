@@ -105,6 +105,10 @@ typedef struct osb_attn_short_args {
   const float* rope_cos;          /* fp32 [Lmax, D/2] or NULL: interleaved-pair RoPE by token    */
   const float* rope_sin;          /*   index (rotary_embedding_torch layout)      */
   float softmax_scale;            /* D^-0.5                                                      */
+  const void* q_norm_w2;          /* optional second RMSNorm weight pair used by tokens >= norm_split: the     */
+  const void* k_norm_w2;          /*   joint txt|img sequence of MMDiT has per-stream QKNorm (layers.py:222,238) */
+  int32_t norm_split;
+  int32_t reserved;
 } osb_attn_short_args;
 
 /* softmax(q k^T * scale) v per (sequence, head), non-causal, optional per-head RMSNorm on q,k
@@ -138,11 +142,12 @@ typedef struct osb_conv3d_args {
 int osb_conv3d_ndhwc(const osb_conv3d_args* args, void* stream);
 
 /* GroupNorm statistics over an NDHWC tensor: for every (n, group) the mean and 1/sqrt(var + eps) over
- * (C/groups) channels x T*H*W positions.  `sums` is a caller-provided fp64 scratch [nb, groups, 2] that the
- * call zeroes, fills by atomics and finalises into mean_rstd fp32 [nb, groups, 2].
+ * (C/groups) channels x T*H*W positions -> mean_rstd fp32 [nb, groups, 2].  Deterministic (no atomics): fp32
+ * partials per 2048-position chunk in `workspace` (osb_group_stats_workspace_bytes), fixed-order fp64 finalisation.
  * Replaces the statistics half of torch.nn.GroupNorm at unet_causal_3d_blocks.py:216,218,246-250; vae.py:115,229. */
+int64_t osb_group_stats_workspace_bytes(int64_t nb, int64_t positions, int32_t groups);
 int osb_group_stats(const void* x, int64_t nb, int64_t positions, int32_t C, int32_t groups, float eps,
-                    double* sums, float* mean_rstd, void* stream);
+                    void* workspace, int64_t workspace_bytes, float* mean_rstd, void* stream);
 
 typedef struct osb_vae_prep_args {
   const void* x;           /* bf16 NDHWC [nb, t, h, w, c]                                                      */

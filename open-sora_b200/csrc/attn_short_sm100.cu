@@ -31,6 +31,8 @@ struct AttnParams {
   int32_t Lq, Lk;
   const int32_t* kv_lens;
   const __nv_bfloat16* qw; const __nv_bfloat16* kw;
+  const __nv_bfloat16* qw2; const __nv_bfloat16* kw2;  // weights for tokens >= norm_split (joint txt|img sequences)
+  int32_t norm_split;
   float eps;
   const float* cos; const float* sin;
   float scale_log2;      // softmax_scale * log2(e)
@@ -223,7 +225,8 @@ __global__ void __launch_bounds__(kAttnThreads, (D <= 72) ? 2 : 1) attn_short_ke
       for (int u = 0; u < U; ++u) ss += sumsq8(tk[u]);
       rk = rsqrtf(ss * (1.0f / D) + p.eps);
     }
-    finish_and_store_units<D, 0, UP>(tk, rk, p.kw, p.cos ? p.cos + (int64_t)ktok * (D / 2) : nullptr,
+    const __nv_bfloat16* kwt = (p.kw2 != nullptr && ktok >= p.norm_split) ? p.kw2 : p.kw;
+    finish_and_store_units<D, 0, UP>(tk, rk, kwt, p.cos ? p.cos + (int64_t)ktok * (D / 2) : nullptr,
                                      p.sin ? p.sin + (int64_t)ktok * (D / 2) : nullptr, sK, k_chunk_bytes, sKt, slot);
     // V^T: raw bf16 halves go straight to their transposed position (no fp32 round trip)
     uint8_t* vt = sVt + (slot >> 6) * vt_chunk_bytes + (slot & 7) * 2;
@@ -287,8 +290,9 @@ __global__ void __launch_bounds__(kAttnThreads, (D <= 72) ? 2 : 1) attn_short_ke
       }
       const float* cq = p.cos ? p.cos + (int64_t)qtok * (D / 2) : nullptr;
       const float* sq = p.sin ? p.sin + (int64_t)qtok * (D / 2) : nullptr;
-      if (part == 0) finish_and_store_units<D, 0, U0>(t, rq, p.qw, cq, sq, sQ, 128 * 128, sQt, r);
-      else finish_and_store_units<D, U0, UP>(t, rq, p.qw, cq, sq, sQ, 128 * 128, sQt, r);
+      const __nv_bfloat16* qwt = (p.qw2 != nullptr && qtok >= p.norm_split) ? p.qw2 : p.qw;
+      if (part == 0) finish_and_store_units<D, 0, U0>(t, rq, qwt, cq, sq, sQ, 128 * 128, sQt, r);
+      else finish_and_store_units<D, U0, UP>(t, rq, qwt, cq, sq, sQ, 128 * 128, sQt, r);
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -485,6 +489,8 @@ extern "C" int osb_attn_short(const osb_attn_short_args* a, void* stream) {
               "osb_attn_short: tensors must be 16-byte aligned");
   OSB_REQUIRE((a->q_norm_w == nullptr) == (a->k_norm_w == nullptr), "osb_attn_short: q/k norm weights must come together");
   OSB_REQUIRE((a->rope_cos == nullptr) == (a->rope_sin == nullptr), "osb_attn_short: rope cos/sin must come together");
+  OSB_REQUIRE((a->q_norm_w2 == nullptr) == (a->k_norm_w2 == nullptr) && (a->q_norm_w2 == nullptr || a->q_norm_w != nullptr),
+              "osb_attn_short: the second norm weight pair needs the first");
   OSB_REQUIRE(a->rope_cos == nullptr || ((reinterpret_cast<uintptr_t>(a->rope_cos) | reinterpret_cast<uintptr_t>(a->rope_sin)) & 15) == 0,
               "osb_attn_short: rope tables must be 16-byte aligned");
 
@@ -500,6 +506,9 @@ extern "C" int osb_attn_short(const osb_attn_short_args* a, void* stream) {
   p.Lq = a->Lq; p.Lk = a->Lk; p.kv_lens = a->kv_lens;
   p.qw = static_cast<const __nv_bfloat16*>(a->q_norm_w);
   p.kw = static_cast<const __nv_bfloat16*>(a->k_norm_w);
+  p.qw2 = static_cast<const __nv_bfloat16*>(a->q_norm_w2);
+  p.kw2 = static_cast<const __nv_bfloat16*>(a->k_norm_w2);
+  p.norm_split = a->norm_split;
   p.eps = a->norm_eps;
   p.cos = a->rope_cos; p.sin = a->rope_sin;
   p.scale_log2 = a->softmax_scale * 1.4426950408889634f;

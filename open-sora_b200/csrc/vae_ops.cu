@@ -14,24 +14,18 @@ namespace osb {
 constexpr int kStatsThreads = 256;
 constexpr int kStatsPositionsPerBlock = 2048;
 
-__global__ void group_stats_zero_kernel(double* sums, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) sums[i] = 0.0;
-}
-
-// grid (position chunks, nb); each thread owns one 8-channel vector index (256 % (C/8) == 0)
+// grid (position chunks, nb); each thread owns one 8-channel vector index (256 % (C/8) == 0).
+// Deterministic: per-thread partials -> shared memory -> fixed-order sum per group -> one fp32 partial per
+// (chunk, n, group); the finalize kernel adds the chunk partials in a fixed order in fp64.  No atomics.
 __global__ void __launch_bounds__(kStatsThreads)
-group_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t positions, int C, int groups, double* __restrict__ sums) {
-  extern __shared__ float sacc[];  // [groups][2]
+group_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t positions, int C, int groups, float* __restrict__ partial) {
+  __shared__ float sp[kStatsThreads][17];
   const int n = blockIdx.y;
   const int vecs = C >> 3;
   const int cg = C / groups;
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
   const int64_t p0 = (int64_t)blockIdx.x * kStatsPositionsPerBlock;
   const int64_t p1 = p0 + kStatsPositionsPerBlock < positions ? p0 + kStatsPositionsPerBlock : positions;
   const uint4* base = reinterpret_cast<const uint4*>(x + (int64_t)n * positions * C);
-  const int v = threadIdx.x % vecs;
   float s[8], q[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
@@ -48,24 +42,45 @@ group_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t positions, int C
     }
   }
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int g = (v * 8 + e) / cg;
-    atomicAdd(&sacc[2 * g], s[e]);
-    atomicAdd(&sacc[2 * g + 1], q[e]);
-  }
+  for (int e = 0; e < 8; ++e) { sp[threadIdx.x][e] = s[e]; sp[threadIdx.x][8 + e] = q[e]; }
   __syncthreads();
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
-    atomicAdd(&sums[(int64_t)n * groups * 2 + i], (double)sacc[i]);
+  for (int g = threadIdx.x; g < groups; g += kStatsThreads) {
+    float ss = 0.f, qq = 0.f;
+    for (int c = g * cg; c < (g + 1) * cg; ++c) {
+      const int v = c >> 3, e = c & 7;
+      for (int t = v; t < kStatsThreads; t += vecs) { ss += sp[t][e]; qq += sp[t][8 + e]; }
+    }
+    float* out = partial + (((int64_t)blockIdx.x * gridDim.y + n) * groups + g) * 2;
+    out[0] = ss;
+    out[1] = qq;
+  }
 }
 
-__global__ void group_stats_finalize_kernel(const double* sums, float* mean_rstd, int n, double count, float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double mean = sums[2 * i] / count;
-  double var = sums[2 * i + 1] / count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  mean_rstd[2 * i] = (float)mean;
-  mean_rstd[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+// one block per (n, group): fixed-order strided sums + tree in fp64
+__global__ void __launch_bounds__(256)
+group_stats_finalize_kernel(const float* __restrict__ partial, float* __restrict__ mean_rstd, int64_t chunks, int ng,
+                            double count, float eps) {
+  __shared__ double rs[256], rq[256];
+  const int i = blockIdx.x;  // n * groups + g
+  double s = 0.0, q = 0.0;
+  for (int64_t c = threadIdx.x; c < chunks; c += 256) {
+    const float2 v = *reinterpret_cast<const float2*>(partial + (c * ng + i) * 2);
+    s += (double)v.x;
+    q += (double)v.y;
+  }
+  rs[threadIdx.x] = s; rq[threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { rs[threadIdx.x] += rs[threadIdx.x + o]; rq[threadIdx.x] += rq[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double mean = rs[0] / count;
+    double var = rq[0] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mean_rstd[2 * i] = (float)mean;
+    mean_rstd[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
 }
 
 struct PrepParams {
@@ -133,23 +148,31 @@ __global__ void __launch_bounds__(256) vae_prep_kernel(const PrepParams p) {
 
 }  // namespace osb
 
+extern "C" int64_t osb_group_stats_workspace_bytes(int64_t nb, int64_t positions, int32_t groups) {
+  const int64_t chunks = (positions + osb::kStatsPositionsPerBlock - 1) / osb::kStatsPositionsPerBlock;
+  return chunks * nb * groups * 2 * (int64_t)sizeof(float);
+}
+
 extern "C" int osb_group_stats(const void* x, int64_t nb, int64_t positions, int32_t C, int32_t groups, float eps,
-                               double* sums, float* mean_rstd, void* stream) {
+                               void* workspace, int64_t workspace_bytes, float* mean_rstd, void* stream) {
   using namespace osb;
   if (!initialised()) { set_error("osb_init() has not been called"); return OSB_ERR_NOT_INIT; }
-  OSB_REQUIRE(x && sums && mean_rstd, "osb_group_stats: null tensor");
+  OSB_REQUIRE(x && workspace && mean_rstd, "osb_group_stats: null tensor");
   OSB_REQUIRE(nb > 0 && positions > 0 && C > 0 && groups > 0 && C % groups == 0, "osb_group_stats: bad shape");
   OSB_REQUIRE(C % 8 == 0 && kStatsThreads % (C / 8) == 0, "osb_group_stats: C/8 must divide %d (C = %d)", kStatsThreads, C);
   OSB_REQUIRE(nb <= 65535 && groups <= 1024, "osb_group_stats: batch / groups too large");
+  OSB_REQUIRE(workspace_bytes >= osb_group_stats_workspace_bytes(nb, positions, groups),
+              "osb_group_stats: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes,
+              (long long)osb_group_stats_workspace_bytes(nb, positions, groups));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int n = (int)(nb * groups);
-  group_stats_zero_kernel<<<(2 * n + 255) / 256, 256, 0, s>>>(sums, 2 * n);
-  const unsigned chunks = (unsigned)((positions + kStatsPositionsPerBlock - 1) / kStatsPositionsPerBlock);
-  group_stats_kernel<<<dim3(chunks, (unsigned)nb), kStatsThreads, groups * 2 * sizeof(float), s>>>(
-      static_cast<const __nv_bfloat16*>(x), positions, C, groups, sums);
-  group_stats_finalize_kernel<<<(n + 255) / 256, 256, 0, s>>>(sums, mean_rstd, n, (double)positions * (C / groups), eps);
+  const int ng = (int)(nb * groups);
+  const int64_t chunks = (positions + kStatsPositionsPerBlock - 1) / kStatsPositionsPerBlock;
+  group_stats_kernel<<<dim3((unsigned)chunks, (unsigned)nb), kStatsThreads, 0, s>>>(
+      static_cast<const __nv_bfloat16*>(x), positions, C, groups, static_cast<float*>(workspace));
+  group_stats_finalize_kernel<<<ng, 256, 0, s>>>(static_cast<const float*>(workspace), mean_rstd, chunks, ng,
+                                                 (double)positions * (C / groups), eps);
   OSB_CHECK_CUDA(cudaGetLastError());
-  count_launch(3);
+  count_launch(2);
   return OSB_OK;
 }
 

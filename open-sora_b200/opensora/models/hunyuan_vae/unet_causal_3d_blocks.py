@@ -64,6 +64,8 @@ class CausalConv3d(nn.Module):
         if not x.is_cuda or x.dtype != torch.bfloat16:
             raise osb.OsbError("hunyuan_vae (osb200) runs on CUDA in bfloat16, channels-last inside; no fallback")
         wp, bp, narrow, cp, cout = self._weights()
+        if x.shape[-1] % 8:  # e.g. a 4-channel latent: zero-pad channels once (weights are zero there too)
+            x = torch.nn.functional.pad(x, (0, -x.shape[-1] % 8))
         nb, T, H, W, C = x.shape
         if self.kernel_size == 1:
             assert norm is None and not silu and up == (1, 1, 1)

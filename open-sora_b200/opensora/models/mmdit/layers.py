@@ -1,0 +1,334 @@
+"""MMDiT layers on the osb200 kernels — same classes, constructor arguments, state-dict keys and the same
+block-`processor` plug-in hook as the reference's `opensora/models/mmdit/layers.py`
+(`DoubleStreamBlock.set_processor / forward = self.processor(self, img, txt, vec, pe)` :295-306,
+`SingleStreamBlock` :378-388).  The nn.Modules hold parameters; the two processor classes below ARE the drop-in:
+they read the block's own parameters and run every FLOP on libosb200 (sm_100a):
+
+  LN(no affine)+modulate -> `osb_ln_modulate`; every Linear -> `osb_gemm_bf16` (bias / GELU-tanh / gate*x+residual
+  epilogues); QK-RMSNorm + RoPE + joint txt|img softmax attention -> `osb_attn_short` (per-stream norm weights via
+  `norm_split`); `linear2(cat(attn, gelu(mlp)))` reads ONE [rows, 5C] buffer that the attention kernel and the
+  GELU GEMM wrote side by side (no torch.cat materialisation).
+
+Limits of this round: the joint sequence must fit the short-key attention kernel (L_txt + L_img <= 320 keys per
+sample; the streaming kernel for L = 8828 is the next kernel on SURVEY.md §8 row a-M) and RoPE must be the Flux
+interleaved layout (`EmbedND`); `LigerEmbedND`'s rotate-half layout raises NotImplementedError."""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+from torch import Tensor, nn
+
+from .math import liger_rope, rope, rope_tables
+
+
+def _osb():
+    import osb200
+
+    return osb200
+
+
+class EmbedND(nn.Module):
+    """layers.py:31-44."""
+
+    def __init__(self, dim: int, theta: int, axes_dim: list[int]):
+        super().__init__()
+        self.dim, self.theta, self.axes_dim = dim, theta, axes_dim
+
+    def forward(self, ids: Tensor) -> Tensor:
+        emb = torch.cat([rope(ids[..., i], self.axes_dim[i], self.theta) for i in range(ids.shape[-1])], dim=-3)
+        return emb.unsqueeze(1)
+
+
+class LigerEmbedND(nn.Module):
+    """layers.py:47-65."""
+
+    def __init__(self, dim: int, theta: int, axes_dim: list[int]):
+        super().__init__()
+        self.dim, self.theta, self.axes_dim = dim, theta, axes_dim
+
+    def forward(self, ids: Tensor):
+        cs = [liger_rope(ids[..., i], self.axes_dim[i], self.theta) for i in range(ids.shape[-1])]
+        cos = torch.cat([c for c, _ in cs], dim=-1).repeat(1, 1, 2).contiguous()
+        sin = torch.cat([s for _, s in cs], dim=-1).repeat(1, 1, 2).contiguous()
+        return (cos, sin)
+
+
+def timestep_embedding(t: Tensor, dim, max_period=10000, time_factor: float = 1000.0):
+    """layers.py:68-88 (the reference `torch.compile`s this; it is [B, 256] work once per step)."""
+    t = time_factor * t
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(t.device)
+    args = t[:, None].float() * freqs[None]
+    emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    if dim % 2:
+        emb = torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1)
+    if torch.is_floating_point(t):
+        emb = emb.to(t)
+    return emb
+
+
+def _linear(x2d: Tensor, lin: nn.Linear, **kw) -> Tensor:
+    return _osb().gemm(x2d, lin.weight, lin.bias, **kw)
+
+
+class MLPEmbedder(nn.Module):
+    def __init__(self, in_dim: int, hidden_dim: int):
+        super().__init__()
+        self.in_layer = nn.Linear(in_dim, hidden_dim, bias=True)
+        self.silu = nn.SiLU()
+        self.out_layer = nn.Linear(hidden_dim, hidden_dim, bias=True)
+
+    def forward(self, x: Tensor) -> Tensor:
+        h = _linear(x.to(self.in_layer.weight.dtype).contiguous(), self.in_layer)
+        return _linear(torch.nn.functional.silu(h), self.out_layer)
+
+
+class RMSNorm(nn.Module):
+    """Parameter container (`scale`), layers.py:102-111; applied inside the attention kernel."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        self.scale = nn.Parameter(torch.ones(dim))
+
+
+class FusedRMSNorm(RMSNorm):
+    pass
+
+
+class QKNorm(nn.Module):
+    def __init__(self, dim: int):
+        super().__init__()
+        self.query_norm = FusedRMSNorm(dim)
+        self.key_norm = FusedRMSNorm(dim)
+
+
+class SelfAttention(nn.Module):
+    """Parameter container with the reference's attribute names (layers.py:138-152)."""
+
+    def __init__(self, dim: int, num_heads: int = 8, qkv_bias: bool = False, fused_qkv: bool = True):
+        super().__init__()
+        self.num_heads, self.fused_qkv = num_heads, fused_qkv
+        if fused_qkv:
+            self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        else:
+            self.q_proj = nn.Linear(dim, dim, bias=qkv_bias)
+            self.k_proj = nn.Linear(dim, dim, bias=qkv_bias)
+            self.v_proj = nn.Linear(dim, dim, bias=qkv_bias)
+        self.norm = QKNorm(dim // num_heads)
+        self.proj = nn.Linear(dim, dim)
+        self._packed = None
+
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        return super()._apply(fn, *a, **k)
+
+    def qkv_weights(self):
+        """[3C, C] weight and [3C] bias in q|k|v row order for ONE GEMM, whichever way the checkpoint stores them."""
+        if self.fused_qkv:
+            return self.qkv.weight, self.qkv.bias
+        if self._packed is None:
+            w = torch.cat([self.q_proj.weight, self.k_proj.weight, self.v_proj.weight], 0).contiguous()
+            b = None if self.q_proj.bias is None else torch.cat([self.q_proj.bias, self.k_proj.bias, self.v_proj.bias], 0).contiguous()
+            self._packed = (w, b)
+        return self._packed
+
+
+@dataclass
+class ModulationOut:
+    shift: Tensor
+    scale: Tensor
+    gate: Tensor
+
+
+class Modulation(nn.Module):
+    def __init__(self, dim: int, double: bool):
+        super().__init__()
+        self.is_double = double
+        self.multiplier = 6 if double else 3
+        self.lin = nn.Linear(dim, self.multiplier * dim, bias=True)
+
+    def forward(self, vec: Tensor):
+        """layers.py:186-192; returns fp32 [B, C] row views (row stride = multiplier*C) the kernels consume directly."""
+        out = _linear(torch.nn.functional.silu(vec).contiguous(), self.lin).float()
+        c = out.chunk(self.multiplier, dim=-1)
+        return ModulationOut(*c[:3]), (ModulationOut(*c[3:]) if self.is_double else None)
+
+
+def _check(x: Tensor):
+    osb = _osb()
+    if not x.is_cuda or x.dtype != torch.bfloat16:
+        raise osb.OsbError("MMDiT (osb200) runs on CUDA in bfloat16 only; there is no CPU / eager fallback")
+    return osb
+
+
+def _rope(pe):
+    cos, sin, half = rope_tables(pe)
+    if half:
+        raise NotImplementedError("rotate-half (LigerEmbedND) RoPE is not built into the osb200 attention kernel yet: "
+                                  "use use_liger_rope=False (math.py:60-65 interleaved layout)")
+    return cos, sin
+
+
+class DoubleStreamBlockProcessor:
+    """osb200 implementation of layers.py:195-253."""
+
+    def __call__(self, attn: nn.Module, img: Tensor, txt: Tensor, vec: Tensor, pe) -> tuple[Tensor, Tensor]:
+        osb = _check(img)
+        B, Li, C = img.shape
+        Lt = txt.shape[1]
+        L, H, D = Lt + Li, attn.num_heads, attn.head_dim
+        im1, im2 = attn.img_mod(vec)
+        tm1, tm2 = attn.txt_mod(vec)
+        img2, txt2 = img.reshape(B * Li, C).contiguous(), txt.reshape(B * Lt, C).contiguous()
+        xi = osb.ln_modulate(img2, im1.shift, im1.scale, group_rows=Li)
+        xt = osb.ln_modulate(txt2, tm1.shift, tm1.scale, group_rows=Lt)
+        # q|k|v of both streams land in ONE joint [B*(Lt+Li), 3C] buffer in txt-then-img token order (layers.py:240-242)
+        qkv = torch.empty(B * L, 3 * C, dtype=img.dtype, device=img.device)
+        wi, bi = attn.img_attn.qkv_weights()
+        wt, bt = attn.txt_attn.qkv_weights()
+        for b in range(B):
+            osb.gemm(xt[b * Lt:(b + 1) * Lt], wt, bt, out=qkv[b * L:b * L + Lt])
+            osb.gemm(xi[b * Li:(b + 1) * Li], wi, bi, out=qkv[b * L + Lt:(b + 1) * L])
+        cos, sin = _rope(pe)
+        ao = torch.empty(B * L, C, dtype=img.dtype, device=img.device)
+        osb.attn_short(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], ao, num_seqs=B, seqs_per_batch=1, q_strides=(L, 0, 1),
+                       k_strides=(L, 0, 1), Lq=L, Lk=L, num_heads=H, head_dim=D,
+                       q_norm_w=attn.txt_attn.norm.query_norm.scale, k_norm_w=attn.txt_attn.norm.key_norm.scale,
+                       q_norm_w2=attn.img_attn.norm.query_norm.scale, k_norm_w2=attn.img_attn.norm.key_norm.scale,
+                       norm_split=Lt, rope_cos=cos, rope_sin=sin)
+        img_o, txt_o = torch.empty_like(img2), torch.empty_like(txt2)
+        for b in range(B):  # x + gate * proj(attn)   (layers.py:247, 251)
+            osb.gemm(ao[b * L + Lt:(b + 1) * L], attn.img_attn.proj.weight, attn.img_attn.proj.bias,
+                     epilogue=osb.EPI_BIAS_GATE_RES, residual=img2[b * Li:(b + 1) * Li], gate=im1.gate[b:b + 1],
+                     out=img_o[b * Li:(b + 1) * Li])
+            osb.gemm(ao[b * L:b * L + Lt], attn.txt_attn.proj.weight, attn.txt_attn.proj.bias,
+                     epilogue=osb.EPI_BIAS_GATE_RES, residual=txt2[b * Lt:(b + 1) * Lt], gate=tm1.gate[b:b + 1],
+                     out=txt_o[b * Lt:(b + 1) * Lt])
+        # x + gate * MLP((1 + scale) * LN(x) + shift)   (layers.py:248, 252)
+        for x_o, mod, mlp, n in ((img_o, im2, attn.img_mlp, Li), (txt_o, tm2, attn.txt_mlp, Lt)):
+            xm = osb.ln_modulate(x_o, mod.shift, mod.scale, group_rows=n)
+            hid = osb.gemm(xm, mlp[0].weight, mlp[0].bias, epilogue=osb.EPI_BIAS_GELU_TANH)
+            osb.gemm(hid, mlp[2].weight, mlp[2].bias, epilogue=osb.EPI_BIAS_GATE_RES, residual=x_o, gate=mod.gate,
+                     group_rows=n, out=x_o)
+        return img_o.view(B, Li, C), txt_o.view(B, Lt, C)
+
+
+class DoubleStreamBlock(nn.Module):
+    def __init__(self, hidden_size: int, num_heads: int, mlp_ratio: float, qkv_bias: bool = False, fused_qkv: bool = True):
+        super().__init__()
+        mlp_hidden_dim = int(hidden_size * mlp_ratio)
+        self.num_heads, self.hidden_size, self.head_dim = num_heads, hidden_size, hidden_size // num_heads
+        self.img_mod = Modulation(hidden_size, double=True)
+        self.img_norm1 = nn.LayerNorm(hidden_size, elementwise_affine=False, eps=1e-6)
+        self.img_attn = SelfAttention(dim=hidden_size, num_heads=num_heads, qkv_bias=qkv_bias, fused_qkv=fused_qkv)
+        self.img_norm2 = nn.LayerNorm(hidden_size, elementwise_affine=False, eps=1e-6)
+        self.img_mlp = nn.Sequential(nn.Linear(hidden_size, mlp_hidden_dim, bias=True), nn.GELU(approximate="tanh"),
+                                     nn.Linear(mlp_hidden_dim, hidden_size, bias=True))
+        self.txt_mod = Modulation(hidden_size, double=True)
+        self.txt_norm1 = nn.LayerNorm(hidden_size, elementwise_affine=False, eps=1e-6)
+        self.txt_attn = SelfAttention(dim=hidden_size, num_heads=num_heads, qkv_bias=qkv_bias, fused_qkv=fused_qkv)
+        self.txt_norm2 = nn.LayerNorm(hidden_size, elementwise_affine=False, eps=1e-6)
+        self.txt_mlp = nn.Sequential(nn.Linear(hidden_size, mlp_hidden_dim, bias=True), nn.GELU(approximate="tanh"),
+                                     nn.Linear(mlp_hidden_dim, hidden_size, bias=True))
+        self.set_processor(DoubleStreamBlockProcessor())
+
+    def set_processor(self, processor) -> None:
+        self.processor = processor
+
+    def get_processor(self):
+        return self.processor
+
+    def forward(self, img: Tensor, txt: Tensor, vec: Tensor, pe, **kwargs) -> tuple[Tensor, Tensor]:
+        return self.processor(self, img, txt, vec, pe)
+
+
+class SingleStreamBlockProcessor:
+    """osb200 implementation of layers.py:309-334."""
+
+    def __call__(self, attn: nn.Module, x: Tensor, vec: Tensor, pe) -> Tensor:
+        osb = _check(x)
+        B, L, C = x.shape
+        H, D, M4 = attn.num_heads, attn.head_dim, attn.mlp_hidden_dim
+        mod, _ = attn.modulation(vec)
+        x2 = x.reshape(B * L, C).contiguous()
+        xm = osb.ln_modulate(x2, mod.shift, mod.scale, group_rows=L)
+        wq, bq, wm, bm = attn.split_weights()
+        qkv = osb.gemm(xm, wq, bq)                                               # [B*L, 3C]
+        cat = torch.empty(B * L, C + M4, dtype=x.dtype, device=x.device)         # [attn | gelu(mlp)] side by side
+        osb.gemm(xm, wm, bm, epilogue=osb.EPI_BIAS_GELU_TANH, out=cat[:, C:])
+        cos, sin = _rope(pe)
+        osb.attn_short(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], cat[:, :C], num_seqs=B, seqs_per_batch=1,
+                       q_strides=(L, 0, 1), k_strides=(L, 0, 1), Lq=L, Lk=L, num_heads=H, head_dim=D,
+                       q_norm_w=attn.norm.query_norm.scale, k_norm_w=attn.norm.key_norm.scale, rope_cos=cos, rope_sin=sin)
+        out = osb.gemm(cat, attn.linear2.weight, attn.linear2.bias, epilogue=osb.EPI_BIAS_GATE_RES, residual=x2,
+                       gate=mod.gate, group_rows=L)
+        return out.view(B, L, C)
+
+
+class SingleStreamBlock(nn.Module):
+    def __init__(self, hidden_size: int, num_heads: int, mlp_ratio: float = 4.0, qk_scale: float | None = None,
+                 fused_qkv: bool = True):
+        super().__init__()
+        self.hidden_dim = self.hidden_size = hidden_size
+        self.num_heads, self.head_dim = num_heads, hidden_size // num_heads
+        self.scale = qk_scale or self.head_dim**-0.5
+        self.fused_qkv = fused_qkv
+        self.mlp_hidden_dim = int(hidden_size * mlp_ratio)
+        if fused_qkv:
+            self.linear1 = nn.Linear(hidden_size, hidden_size * 3 + self.mlp_hidden_dim)
+        else:
+            self.q_proj = nn.Linear(hidden_size, hidden_size)
+            self.k_proj = nn.Linear(hidden_size, hidden_size)
+            self.v_mlp = nn.Linear(hidden_size, hidden_size + self.mlp_hidden_dim)
+        self.linear2 = nn.Linear(hidden_size + self.mlp_hidden_dim, hidden_size)
+        self.norm = QKNorm(self.head_dim)
+        self.pre_norm = nn.LayerNorm(hidden_size, elementwise_affine=False, eps=1e-6)
+        self.mlp_act = nn.GELU(approximate="tanh")
+        self.modulation = Modulation(hidden_size, double=False)
+        self._packed = None
+        self.set_processor(SingleStreamBlockProcessor())
+
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        return super()._apply(fn, *a, **k)
+
+    def split_weights(self):
+        """(W_qkv [3C,C], b_qkv, W_mlp [4C,C], b_mlp): row views of linear1, or packed from q_proj/k_proj/v_mlp."""
+        C = self.hidden_size
+        if self.fused_qkv:
+            w, b = self.linear1.weight, self.linear1.bias
+            return w[:3 * C], b[:3 * C], w[3 * C:], b[3 * C:]
+        if self._packed is None:
+            wq = torch.cat([self.q_proj.weight, self.k_proj.weight, self.v_mlp.weight[:C]], 0).contiguous()
+            bq = torch.cat([self.q_proj.bias, self.k_proj.bias, self.v_mlp.bias[:C]], 0).contiguous()
+            self._packed = (wq, bq, self.v_mlp.weight[C:], self.v_mlp.bias[C:])
+        return self._packed
+
+    def set_processor(self, processor) -> None:
+        self.processor = processor
+
+    def get_processor(self):
+        return self.processor
+
+    def forward(self, x: Tensor, vec: Tensor, pe, **kwargs) -> Tensor:
+        return self.processor(self, x, vec, pe)
+
+
+class LastLayer(nn.Module):
+    """layers.py:391-402."""
+
+    def __init__(self, hidden_size: int, patch_size: int, out_channels: int):
+        super().__init__()
+        self.norm_final = nn.LayerNorm(hidden_size, elementwise_affine=False, eps=1e-6)
+        self.linear = nn.Linear(hidden_size, patch_size * patch_size * out_channels, bias=True)
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size, 2 * hidden_size, bias=True))
+
+    def forward(self, x: Tensor, vec: Tensor) -> Tensor:
+        osb = _check(x)
+        B, L, C = x.shape
+        m = _linear(torch.nn.functional.silu(vec).contiguous(), self.adaLN_modulation[1]).float()
+        shift, scale = m.chunk(2, dim=1)
+        xm = osb.ln_modulate(x.reshape(B * L, C).contiguous(), shift, scale, group_rows=L)
+        return _linear(xm, self.linear).view(B, L, -1)

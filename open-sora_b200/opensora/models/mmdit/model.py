@@ -1,0 +1,160 @@
+"""MMDiTModel / `Flux` factory with the reference's constructor, registry key ("flux"), forward signature and
+state-dict keys (`opensora/models/mmdit/model.py:38-303`), running on the osb200 kernels.  Forward-only:
+`grad_ckpt_settings` is accepted and ignored (activation checkpointing is training-only)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+from torch import Tensor, nn
+
+from opensora.registry import MODELS
+
+from .layers import (DoubleStreamBlock, EmbedND, LastLayer, LigerEmbedND, MLPEmbedder, SingleStreamBlock, _linear,
+                     timestep_embedding)
+
+
+@dataclass
+class MMDiTConfig:
+    model_type = "MMDiT"
+    from_pretrained: str
+    cache_dir: str
+    in_channels: int
+    vec_in_dim: int
+    context_in_dim: int
+    hidden_size: int
+    mlp_ratio: float
+    num_heads: int
+    depth: int
+    depth_single_blocks: int
+    axes_dim: list
+    theta: int
+    qkv_bias: bool
+    guidance_embed: bool
+    cond_embed: bool = False
+    fused_qkv: bool = True
+    grad_ckpt_settings: tuple | None = None
+    use_liger_rope: bool = False
+    patch_size: int = 2
+
+    def get(self, attribute_name, default=None):
+        return getattr(self, attribute_name, default)
+
+    def __contains__(self, attribute_name):
+        return hasattr(self, attribute_name)
+
+
+class MMDiTModel(nn.Module):
+    config_class = MMDiTConfig
+
+    def __init__(self, config: MMDiTConfig):
+        super().__init__()
+        self.config = config
+        self.in_channels = self.out_channels = config.in_channels
+        self.patch_size = config.patch_size
+        if config.hidden_size % config.num_heads != 0:
+            raise ValueError(f"Hidden size {config.hidden_size} must be divisible by num_heads {config.num_heads}")
+        pe_dim = config.hidden_size // config.num_heads
+        if sum(config.axes_dim) != pe_dim:
+            raise ValueError(f"Got {config.axes_dim} but expected positional dim {pe_dim}")
+        self.hidden_size, self.num_heads = config.hidden_size, config.num_heads
+        self.pe_embedder = (LigerEmbedND if config.use_liger_rope else EmbedND)(dim=pe_dim, theta=config.theta,
+                                                                                 axes_dim=config.axes_dim)
+        self.img_in = nn.Linear(self.in_channels, self.hidden_size, bias=True)
+        self.time_in = MLPEmbedder(in_dim=256, hidden_dim=self.hidden_size)
+        self.vector_in = MLPEmbedder(config.vec_in_dim, self.hidden_size)
+        self.guidance_in = MLPEmbedder(in_dim=256, hidden_dim=self.hidden_size) if config.guidance_embed else nn.Identity()
+        self.cond_in = nn.Linear(self.in_channels + self.patch_size**2, self.hidden_size, bias=True) \
+            if config.cond_embed else nn.Identity()
+        self.txt_in = nn.Linear(config.context_in_dim, self.hidden_size)
+        self.double_blocks = nn.ModuleList([
+            DoubleStreamBlock(self.hidden_size, self.num_heads, mlp_ratio=config.mlp_ratio, qkv_bias=config.qkv_bias,
+                              fused_qkv=config.fused_qkv) for _ in range(config.depth)])
+        self.single_blocks = nn.ModuleList([
+            SingleStreamBlock(self.hidden_size, self.num_heads, mlp_ratio=config.mlp_ratio, fused_qkv=config.fused_qkv)
+            for _ in range(config.depth_single_blocks)])
+        self.final_layer = LastLayer(self.hidden_size, 1, self.out_channels)
+        self.initialize_weights()
+        self.forward = self.forward_ckpt  # the reference rebinds forward the same way (model.py:143-146)
+        self._input_requires_grad = False
+        self._cond_w = None
+
+    def _apply(self, fn, *a, **k):
+        self._cond_w = None
+        return super()._apply(fn, *a, **k)
+
+    def initialize_weights(self):
+        if self.config.cond_embed:
+            nn.init.zeros_(self.cond_in.weight)
+            nn.init.zeros_(self.cond_in.bias)
+
+    def _lin3(self, x: Tensor, lin: nn.Linear, **kw) -> Tensor:
+        """Linear over a [B, L, K] tensor; K is zero-padded to a multiple of 8 when needed (cond_in: K = 68)."""
+        B, L, K = x.shape
+        x2 = x.to(lin.weight.dtype).reshape(B * L, K)
+        w = lin.weight
+        if K % 8:
+            pad = -K % 8
+            x2 = torch.nn.functional.pad(x2, (0, pad))
+            if self._cond_w is None or self._cond_w[0] is not lin:
+                self._cond_w = (lin, torch.nn.functional.pad(lin.weight, (0, pad)).contiguous())
+            w = self._cond_w[1]
+        import osb200
+
+        return osb200.gemm(x2.contiguous(), w, lin.bias, **kw).view(B, L, -1)
+
+    def prepare_block_inputs(self, img: Tensor, img_ids: Tensor, txt: Tensor, txt_ids: Tensor, timesteps: Tensor,
+                             y_vec: Tensor, cond: Tensor = None, guidance: Tensor | None = None):
+        """model.py:154-202."""
+        if img.ndim != 3 or txt.ndim != 3:
+            raise ValueError("Input img and txt tensors must have 3 dimensions.")
+        dt = self.img_in.weight.dtype
+        img = self._lin3(img, self.img_in)
+        if self.config.cond_embed:
+            if cond is None:
+                raise ValueError("Didn't get conditional input for conditional model.")
+            B, L, C = img.shape
+            import osb200
+
+            img = self._lin3(cond, self.cond_in, epilogue=osb200.EPI_BIAS_GATE_RES, residual=img.reshape(B * L, C))
+        vec = self.time_in(timestep_embedding(timesteps, 256).to(dt))
+        if self.config.guidance_embed:
+            if guidance is None:
+                raise ValueError("Didn't get guidance strength for guidance distilled model.")
+            vec = vec + self.guidance_in(timestep_embedding(guidance, 256).to(dt))
+        vec = vec + self.vector_in(y_vec)
+        txt = self._lin3(txt, self.txt_in)
+        ids = torch.cat((txt_ids, img_ids), dim=1)
+        pe = self.pe_embedder(ids)
+        return img, txt, vec, pe
+
+    def forward_ckpt(self, img: Tensor, img_ids: Tensor, txt: Tensor, txt_ids: Tensor, timesteps: Tensor, y_vec: Tensor,
+                     cond: Tensor = None, guidance: Tensor | None = None, **kwargs) -> Tensor:
+        """model.py:208-233."""
+        img, txt, vec, pe = self.prepare_block_inputs(img, img_ids, txt, txt_ids, timesteps, y_vec, cond, guidance)
+        for block in self.double_blocks:
+            img, txt = block(img, txt, vec, pe)
+        img = torch.cat((txt, img), 1)
+        for block in self.single_blocks:
+            img = block(img, vec, pe)
+        img = img[:, txt.shape[1]:, ...]
+        return self.final_layer(img, vec)
+
+    forward_selective_ckpt = forward_ckpt
+
+
+@MODELS.register_module("flux")
+def Flux(cache_dir: str = None, from_pretrained: str = None, device_map: str | torch.device = "cuda",
+         torch_dtype: torch.dtype = torch.bfloat16, strict_load: bool = False, **kwargs) -> MMDiTModel:
+    """model.py:271-303 (checkpoint loading: local safetensors / torch files only — no hub access offline)."""
+    config = MMDiTConfig(from_pretrained=from_pretrained, cache_dir=cache_dir, **kwargs)
+    model = MMDiTModel(config)
+    if from_pretrained:
+        if from_pretrained.endswith(".safetensors"):
+            from safetensors.torch import load_file
+
+            sd = load_file(from_pretrained)
+        else:
+            sd = torch.load(from_pretrained, map_location="cpu")
+        model.load_state_dict(sd, strict=strict_load)
+    return model.to(device=device_map, dtype=torch_dtype)

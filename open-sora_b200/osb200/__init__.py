@@ -23,6 +23,7 @@ EXPORTS = (
     "osb_attn_short",
     "osb_conv3d_ndhwc",
     "osb_group_stats",
+    "osb_group_stats_workspace_bytes",
     "osb_vae_prep",
 )
 
@@ -55,7 +56,9 @@ def _load() -> C.CDLL:
     lib.osb_conv3d_ndhwc.argtypes = [C.c_void_p, C.c_void_p]
     lib.osb_vae_prep.argtypes = [C.c_void_p, C.c_void_p]
     lib.osb_group_stats.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
-                                    C.c_void_p, C.c_void_p]
+                                    C.c_int64, C.c_void_p, C.c_void_p]
+    lib.osb_group_stats_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int32]
+    lib.osb_group_stats_workspace_bytes.restype = C.c_int64
     return lib
 
 
@@ -128,6 +131,7 @@ class AttnShortArgs(C.Structure):
         ("norm_eps", C.c_float),
         ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
         ("softmax_scale", C.c_float),
+        ("q_norm_w2", C.c_void_p), ("k_norm_w2", C.c_void_p), ("norm_split", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -258,7 +262,8 @@ def gemm(a, w, bias=None, *, epilogue: int = EPI_BIAS, residual=None, gate=None,
 
 def attn_short(q, k, v, out, *, num_seqs: int, seqs_per_batch: int, q_strides, k_strides, Lq: int, Lk: int,
                num_heads: int, head_dim: int, kv_lens=None, q_norm_w=None, k_norm_w=None, norm_eps: float = 1e-6,
-               rope_cos=None, rope_sin=None, softmax_scale: float | None = None):
+               rope_cos=None, rope_sin=None, softmax_scale: float | None = None, q_norm_w2=None, k_norm_w2=None,
+               norm_split: int = 0):
     """softmax(q k^T * scale) v per (sequence, head) with optional fused QK-RMSNorm and RoPE.
     q/k/v/out are 2-D bf16 views [rows, ld]; *_strides = (batch, seq, token) strides in rows."""
     import torch
@@ -282,6 +287,10 @@ def attn_short(q, k, v, out, *, num_seqs: int, seqs_per_batch: int, q_strides, k
     a.rope_cos = rope_cos.data_ptr() if rope_cos is not None else None
     a.rope_sin = rope_sin.data_ptr() if rope_sin is not None else None
     a.softmax_scale = softmax_scale if softmax_scale is not None else head_dim ** -0.5
+    _need(q_norm_w2, torch.bfloat16, "q_norm_w2"); _need(k_norm_w2, torch.bfloat16, "k_norm_w2")
+    a.q_norm_w2 = q_norm_w2.data_ptr() if q_norm_w2 is not None else None
+    a.k_norm_w2 = k_norm_w2.data_ptr() if k_norm_w2 is not None else None
+    a.norm_split = norm_split
     with _Timed("attn_short", 4.0 * num_seqs * Lq * Lk * num_heads * head_dim):  # QK^T + PV FLOPs
         _check(_lib.osb_attn_short(C.byref(a), _stream()), "osb_attn_short")
     return out
@@ -296,10 +305,12 @@ def group_stats(x, groups: int, eps: float = 1e-6):
     assert x.dim() == 5 and x.is_contiguous()
     nb, Cc = x.shape[0], x.shape[-1]
     pos = x.shape[1] * x.shape[2] * x.shape[3]
-    sums = torch.empty(nb, groups, 2, dtype=torch.float64, device=x.device)
+    ws_bytes = int(_lib.osb_group_stats_workspace_bytes(nb, pos, groups))
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=x.device)
     out = torch.empty(nb, groups, 2, dtype=torch.float32, device=x.device)
     with _Timed("group_stats", 2.0 * x.numel()):  # algorithmic bytes: one read
-        _check(_lib.osb_group_stats(_ptr(x), nb, pos, Cc, groups, eps, _ptr(sums), _ptr(out), _stream()), "osb_group_stats")
+        _check(_lib.osb_group_stats(_ptr(x), nb, pos, Cc, groups, eps, _ptr(ws), ws_bytes, _ptr(out), _stream()),
+               "osb_group_stats")
     return out
 
 

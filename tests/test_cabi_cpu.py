@@ -60,9 +60,10 @@ def test_ctypes_struct_layout_matches_header():
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, "probe.c")
         with open(src, "w") as f:
-            f.write('#include <stdio.h>\n#include <stddef.h>\n#include "osb200.h"\nint main(){printf("%zu %zu %zu %zu\\n",'
+            f.write('#include <stdio.h>\n#include <stddef.h>\n#include "osb200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                     "sizeof(osb_gemm_args), sizeof(osb_attn_short_args), offsetof(osb_gemm_args, epilogue),"
-                    "offsetof(osb_attn_short_args, softmax_scale));return 0;}\n")
+                    "offsetof(osb_attn_short_args, softmax_scale), sizeof(osb_conv3d_args), sizeof(osb_vae_prep_args),"
+                    "offsetof(osb_conv3d_args, block_n), offsetof(osb_vae_prep_args, cp));return 0;}\n")
         exe = os.path.join(d, "probe")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
         sizes = [int(v) for v in subprocess.check_output([exe]).split()]
@@ -70,6 +71,10 @@ def test_ctypes_struct_layout_matches_header():
     assert ctypes.sizeof(osb200.AttnShortArgs) == sizes[1]
     assert osb200.GemmArgs.epilogue.offset == sizes[2]
     assert osb200.AttnShortArgs.softmax_scale.offset == sizes[3]
+    assert ctypes.sizeof(osb200.Conv3dArgs) == sizes[4]
+    assert ctypes.sizeof(osb200.VaePrepArgs) == sizes[5]
+    assert osb200.Conv3dArgs.block_n.offset == sizes[6]
+    assert osb200.VaePrepArgs.cp.offset == sizes[7]
 
 
 def test_registry_and_state_dict_contract():

@@ -131,13 +131,23 @@ def test_encoder_decoder_against_reference_goldens(osb):
     m.encoder.load_state_dict({k[4:]: v for k, v in G.items() if k.startswith("enc.")})
     m.decoder.load_state_dict({k[4:]: v for k, v in G.items() if k.startswith("dec.")})
     m = m.cuda().to(torch.bfloat16)
+    from oracle import vae_oracle as V
+    from tests.util import rel_l2
+
+    down, up = V.stage_plan(4, 4, 8)
+    # noise floor: the reference arithmetic itself (oracle restatement) run in bf16 on the same inputs / weights
+    Wb = {k: v.cuda().to(torch.bfloat16) for k, v in G.items()}
+    ze_bf = V.encoder({k[4:]: v for k, v in Wb.items() if k.startswith("enc.")}, Wb["enc_x"], groups=4, strides=down)
+    yd_bf = V.decoder({k[4:]: v for k, v in Wb.items() if k.startswith("dec.")}, Wb["enc_y"][:, :4], groups=4, factors=up)
+    fe, fd = rel_l2(ze_bf, G["enc_y"].cuda()), rel_l2(yd_bf, G["dec_y"].cuda())
+    print(f"[parity] reference-in-bf16 noise floor: encoder {fe:.3e} decoder {fd:.3e}")
     xin = m._to_ndhwc(G["enc_x"].cuda().to(torch.bfloat16), cpad=8)
     z = m._to_ncdhw(m.encoder(xin))
     r, _ = report("encoder vs reference golden", z, G["enc_y"].cuda())
-    assert z.shape == G["enc_y"].shape and r < 2e-2
+    assert z.shape == G["enc_y"].shape and r < max(1.5 * fe, 1e-2)
     y = m._to_ncdhw(m.decoder(m._to_ndhwc(G["enc_y"][:, :4].cuda().to(torch.bfloat16))))
     r, _ = report("decoder vs reference golden", y, G["dec_y"].cuda())
-    assert y.shape == G["dec_y"].shape and r < 2e-2
+    assert y.shape == G["dec_y"].shape and r < max(1.5 * fd, 1e-2)
 
 
 def test_autoencoder_roundtrip_api(osb):
@@ -152,7 +162,7 @@ def test_autoencoder_roundtrip_api(osb):
         assert list(z.shape) == [1, 16] + m.get_latent_size([9, 64, 64])
         x_rec, posterior, z2 = m(x, sample_posterior=False)
     assert x_rec.shape == x.shape and torch.isfinite(x_rec).all()
-    torch.testing.assert_close(z, z2)
+    assert torch.equal(z, z2), "encode must be run-to-run deterministic"
     # causality: perturbing the LAST frame group must not change the reconstruction of earlier latent frames
     x2 = x.clone()
     x2[:, :, 5:] += 0.5
