@@ -175,6 +175,49 @@ def host_inputs(seed):
                 height=torch.tensor([256.0]), width=torch.tensor([256.0]))
 
 
+def vae_leg():
+    """Second half of BASELINE.json's metric: causal 3D VAE encode / decode fps on a synthetic 65x720x1280 video
+    (configs[2]), untiled, bf16, one B200; per-family device times from the same CUDA-event hook as the roofline."""
+    import osb200
+    from tests.vae_bench import DEC_TF, ENC_TF, run
+
+    del_model = torch.cuda.empty_cache
+    del_model()
+    try:
+        res = run(65, 720, 1280, iters=2)
+        osb200.start_profile()
+        from opensora.registry import MODELS, build_module
+
+        torch.manual_seed(0)
+        m = build_module(dict(type="hunyuan_vae"), MODELS, device_map="cuda").eval()
+        with torch.no_grad():
+            z = torch.randn(1, 16, 17, 90, 160, device="cuda").to(torch.bfloat16)
+            m.decode(z)
+            osb200.stop_profile()
+            osb200.start_profile()
+            m.decode(z)
+        fam = {}
+        for name, work, t in osb200.stop_profile():
+            f = fam.setdefault(name, [0, 0.0])
+            f[0] += 1
+            f[1] += t
+        res["decode_families_ms"] = {k: {"launches": v[0], "ms": round(v[1], 2)} for k, v in fam.items()}
+        conv_ms = fam.get("conv3d", [0, 1.0])[1]
+        pk = peaks()
+        res["conv_roofline"] = {"bound": "tensor", "kernel": "gemm_bf16_kernel<conv> (all conv3d launches of one decode)",
+                                "achieved": DEC_TF / (conv_ms * 1e-3), "peak": pk["sustained"], "unit": "TFLOP/s",
+                                "frac": DEC_TF / (conv_ms * 1e-3) / pk["sustained"],
+                                "note": "algorithmic conv FLOPs (1017.9 TF, SURVEY.md 8d) / summed conv3d device time"}
+        res["config"] = {"workload": "hunyuan causal 3D VAE, video 1x3x65x720x1280 <-> latent 1x16x17x90x160, untiled, bf16",
+                         "algorithmic_conv_tflop": {"encode": ENC_TF, "decode": DEC_TF},
+                         "mid_block_attention": "torch SDPA per frame prefix (library kernel; osb200 D=512 kernel pending)"}
+        del m
+        torch.cuda.empty_cache()
+        return res
+    except Exception as e:  # the headline metric above must survive a VAE-leg failure
+        return {"error": repr(e)[:300]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -185,6 +228,7 @@ def main():
                     help="N>1: sp = one sample sequence-sharded over ranks (strong scaling, north_star scheme); "
                          "dp = one sample per rank (weak scaling, no collective)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vae", action="store_true", help="skip the VAE leg (encode/decode fps of BASELINE.json's metric)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "osb200" else args.warmup
 
@@ -290,6 +334,9 @@ def main():
             "families": {k: {"launches_per_step": v[2] // 2, "ms_per_step": v[1] / 2,
                              ("tflops" if k != "ln_modulate" else "gbs"): (v[0] / (v[1] * 1e-3) / (1e12 if k != "ln_modulate" else 1e9))}
                          for k, v in fam.items()}}
+    vae = None
+    if not args.no_vae and world == 1:
+        vae = vae_leg()
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         v, cores, sample = cpu_reference_step()
@@ -305,7 +352,7 @@ def main():
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_out.numel() * 4,
                 "ms_per_step": ms_e2e / args.steps},
-        "roofline": roof, "cpu_baseline": cpu,
+        "roofline": roof, "cpu_baseline": cpu, "vae": vae,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -79,6 +79,22 @@ def main():
         randomize(ll)
         out.update({f"last.{n}": p.detach() for n, p in ll.state_dict().items()})
         out.update(last_out=ll(img, vec))
+        # --- tiny full model (prepare_block_inputs + blocks + final layer), executed by the reference ---------
+        _, _, model_m = layers, math_m, ref_loader.load_mmdit()[2]
+        cfg = dict(in_channels=8, vec_in_dim=12, context_in_dim=20, hidden_size=C, mlp_ratio=4.0, num_heads=Hh, depth=1,
+                   depth_single_blocks=1, axes_dim=axes, theta=10000, qkv_bias=True, guidance_embed=True, cond_embed=True,
+                   fused_qkv=True)
+        fm = model_m.Flux(device_map="cpu", torch_dtype=torch.float32, **cfg)
+        randomize(fm)
+        nn_init = torch.nn.init.normal_
+        nn_init(fm.cond_in.weight, std=0.05)
+        m_img, m_cond = torch.randn(B, Li, 8), torch.randn(B, Li, 12)
+        m_txt, m_y = torch.randn(B, Lt, 20), torch.randn(B, 12)
+        m_t, m_g = torch.tensor([0.3, 0.8]), torch.tensor([4.0, 7.5])
+        img_ids, txt_ids = ids[:, Lt:], ids[:, :Lt]
+        m_out = fm(img=m_img, img_ids=img_ids, txt=m_txt, txt_ids=txt_ids, timesteps=m_t, y_vec=m_y, cond=m_cond, guidance=m_g)
+        out.update({f"model.{n}": p.detach() for n, p in fm.state_dict().items()})
+        out.update(model_img=m_img, model_cond=m_cond, model_txt=m_txt, model_y=m_y, model_t=m_t, model_g=m_g, model_out=m_out)
     arrs = {k: v.detach().float().numpy().astype(np.float32) for k, v in out.items()}
     path = os.path.join(HERE, "mmdit_blocks.npz")
     np.savez_compressed(path, **arrs)

@@ -192,3 +192,13 @@ def test_mid_block_and_encoder_decoder_match_reference():
     torch.testing.assert_close(z, GV["enc_y"], rtol=1e-3, atol=1e-3)
     y = V.decoder(_wv("dec"), GV["enc_y"][:, :4], groups=4, factors=up)
     torch.testing.assert_close(y, GV["dec_y"], rtol=1e-3, atol=1e-3)
+
+
+def test_mmdit_full_model_matches_reference():
+    """model.py:154-233 executed by the reference on a tiny config -> pins oracle M.model_forward."""
+    cfg = dict(num_heads=H, depth=1, depth_single_blocks=1, axes_dim=AXES, theta=10000, guidance_embed=True,
+               cond_embed=True, fused_qkv=True)
+    Lt = G["txt"].shape[1]
+    out = M.model_forward(_w("model"), cfg, G["model_img"], G["ids"][:, Lt:], G["model_txt"], G["ids"][:, :Lt],
+                          G["model_t"], G["model_y"], cond=G["model_cond"], guidance=G["model_g"])
+    torch.testing.assert_close(out, G["model_out"], rtol=1e-4, atol=1e-4)
