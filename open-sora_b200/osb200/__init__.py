@@ -28,6 +28,7 @@ EXPORTS = (
 )
 
 EPI_BIAS, EPI_BIAS_GELU_TANH, EPI_BIAS_GATE_RES = 0, 1, 2
+ATTN_IMPL = int(os.environ.get("OSB_ATTN_IMPL", "0"))  # experiment switch for osb_attn_short's implementation
 
 
 class OsbError(RuntimeError):
@@ -263,7 +264,7 @@ def gemm(a, w, bias=None, *, epilogue: int = EPI_BIAS, residual=None, gate=None,
 def attn_short(q, k, v, out, *, num_seqs: int, seqs_per_batch: int, q_strides, k_strides, Lq: int, Lk: int,
                num_heads: int, head_dim: int, kv_lens=None, q_norm_w=None, k_norm_w=None, norm_eps: float = 1e-6,
                rope_cos=None, rope_sin=None, softmax_scale: float | None = None, q_norm_w2=None, k_norm_w2=None,
-               norm_split: int = 0):
+               norm_split: int = 0, impl: int = 0):
     """softmax(q k^T * scale) v per (sequence, head) with optional fused QK-RMSNorm and RoPE.
     q/k/v/out are 2-D bf16 views [rows, ld]; *_strides = (batch, seq, token) strides in rows."""
     import torch
@@ -291,6 +292,7 @@ def attn_short(q, k, v, out, *, num_seqs: int, seqs_per_batch: int, q_strides, k
     a.q_norm_w2 = q_norm_w2.data_ptr() if q_norm_w2 is not None else None
     a.k_norm_w2 = k_norm_w2.data_ptr() if k_norm_w2 is not None else None
     a.norm_split = norm_split
+    a.reserved = impl if impl else ATTN_IMPL  # 0 = library default; 1 resident keys, 2 flash (P via smem), 3 flash (P in TMEM)
     with _Timed("attn_short", 4.0 * num_seqs * Lq * Lk * num_heads * head_dim):  # QK^T + PV FLOPs
         _check(_lib.osb_attn_short(C.byref(a), _stream()), "osb_attn_short")
     return out

@@ -37,7 +37,9 @@ def cross():
                    Lq=N, Lk=Ly, num_heads=H, head_dim=D, kv_lens=lens)
 
 
-for name, fn, flops in (("spatial", spatial, 4 * N * S * C), ("temporal", temporal, 4 * N * T * C), ("cross", cross, 4 * N * Ly * C)):
+for impl in ([int(v) for v in sys.argv[1:]] or [0]):
+  osb.ATTN_IMPL = impl
+  for name, fn, flops in (("spatial", spatial, 4 * N * S * C), ("temporal", temporal, 4 * N * T * C), ("cross", cross, 4 * N * Ly * C)):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -48,4 +50,4 @@ for name, fn, flops in (("spatial", spatial, 4 * N * S * C), ("temporal", tempor
     e.record()
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / 10
-    print(f"attn {name:9s}: {ms*1e3:8.1f} us  {flops/(ms*1e-3)/1e12:6.1f} TF/s")
+    print(f"attn impl{impl} {name:9s}: {ms*1e3:8.1f} us  {flops/(ms*1e-3)/1e12:6.1f} TF/s")

@@ -178,9 +178,13 @@ def _rope_tables(L, D):
     return ang.cos().contiguous(), ang.sin().contiguous()
 
 
+IMPLS = [1, 2, 3]  # resident keys, flash with P through smem, flash with P in TMEM
+
+
+@pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("D,H", [(72, 4), (64, 3), (128, 2)])
 @pytest.mark.parametrize("mode", ["spatial", "temporal"])
-def test_attn_self(osb, D, H, mode):
+def test_attn_self(osb, D, H, mode, impl):
     B, T, S = 2, 16, 256
     if mode == "temporal":
         T, S = 64, 24
@@ -195,23 +199,24 @@ def test_attn_self(osb, D, H, mode):
     if mode == "spatial":
         strides = (N, S, 1)
         osb.attn_short(q2, k2, v2, out, num_seqs=B * T, seqs_per_batch=T, q_strides=strides, k_strides=strides,
-                       Lq=S, Lk=S, num_heads=H, head_dim=D, q_norm_w=qw, k_norm_w=kw)
+                       Lq=S, Lk=S, num_heads=H, head_dim=D, q_norm_w=qw, k_norm_w=kw, impl=impl)
         x = qkv.float().view(B * T, S, 3, H, D).permute(2, 0, 3, 1, 4)
         ref = _attn_ref(x[0], x[1], x[2], qw, kw, None, None, D ** -0.5)       # [B*T, H, S, D]
         ref = ref.permute(0, 2, 1, 3).reshape(B * N, C)
     else:
         strides = (N, 1, S)
         osb.attn_short(q2, k2, v2, out, num_seqs=B * S, seqs_per_batch=S, q_strides=strides, k_strides=strides,
-                       Lq=T, Lk=T, num_heads=H, head_dim=D, q_norm_w=qw, k_norm_w=kw, rope_cos=cos, rope_sin=sin)
+                       Lq=T, Lk=T, num_heads=H, head_dim=D, q_norm_w=qw, k_norm_w=kw, rope_cos=cos, rope_sin=sin, impl=impl)
         x = qkv.float().view(B, T, S, 3, H, D).permute(3, 0, 2, 4, 1, 5).reshape(3, B * S, H, T, D)
         ref = _attn_ref(x[0], x[1], x[2], qw, kw, cos, sin, D ** -0.5)          # [B*S, H, T, D]
         ref = ref.view(B, S, H, T, D).permute(0, 3, 1, 2, 4).reshape(B * N, C)
-    r, _ = report(f"attn {mode} D{D}", out, ref)
+    r, _ = report(f"attn {mode} D{D} impl{impl}", out, ref)
     assert r < 4e-3
 
 
+@pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("Ly", [300, 77])
-def test_attn_cross(osb, Ly):
+def test_attn_cross(osb, Ly, impl):
     B, N, H, D = 2, 640, 4, 72
     C = H * D
     q = _randn(B * N, C, seed=24)
@@ -219,12 +224,40 @@ def test_attn_cross(osb, Ly):
     lens = torch.tensor([Ly, max(1, Ly // 3)], device="cuda", dtype=torch.int32)
     out = torch.zeros(B * N, C, dtype=torch.bfloat16, device="cuda")
     osb.attn_short(q, kv[:, :C], kv[:, C:], out, num_seqs=B, seqs_per_batch=1, q_strides=(N, 0, 1),
-                   k_strides=(Ly, 0, 1), Lq=N, Lk=Ly, num_heads=H, head_dim=D, kv_lens=lens)
+                   k_strides=(Ly, 0, 1), Lq=N, Lk=Ly, num_heads=H, head_dim=D, kv_lens=lens, impl=impl)
     qf = q.float().view(B, N, H, D).permute(0, 2, 1, 3)
     kvf = kv.float().view(B, Ly, 2, H, D).permute(2, 0, 3, 1, 4)
     ref = _attn_ref(qf, kvf[0], kvf[1], None, None, None, None, D ** -0.5, kv_len=lens)
     ref = ref.permute(0, 2, 1, 3).reshape(B * N, C)
-    r, _ = report(f"attn cross Ly{Ly}", out, ref)
+    r, _ = report(f"attn cross Ly{Ly} impl{impl}", out, ref)
+    assert r < 4e-3
+
+
+@pytest.mark.parametrize("impl", [2, 3])
+@pytest.mark.parametrize("D", [72, 128])
+def test_attn_long_sequence(osb, D, impl):
+    """Streaming path: many key blocks per query tile (online softmax + O rescaling), L not a multiple of anything."""
+    H, nseq, L = 2, 2, 1000
+    C = H * D
+    qkv = _randn(nseq * L, 3 * C, seed=31)
+    qw, kw = _randn(D, seed=32) * 0.2 + 1, _randn(D, seed=33) * 0.2 + 1
+    qw2, kw2 = _randn(D, seed=34) * 0.2 + 1, _randn(D, seed=35) * 0.2 + 1
+    cos, sin = _rope_tables(L, D)
+    out = torch.zeros(nseq * L, C, dtype=torch.bfloat16, device="cuda")
+    split = 100
+    osb.attn_short(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], out, num_seqs=nseq, seqs_per_batch=1, q_strides=(L, 0, 1),
+                   k_strides=(L, 0, 1), Lq=L, Lk=L, num_heads=H, head_dim=D, q_norm_w=qw, k_norm_w=kw, q_norm_w2=qw2,
+                   k_norm_w2=kw2, norm_split=split, rope_cos=cos, rope_sin=sin, impl=impl)
+    x = qkv.float().view(nseq, L, 3, H, D).permute(2, 0, 3, 1, 4)
+
+    def rms(t, w1, w2):
+        n = t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + 1e-6)
+        w = torch.where((torch.arange(L, device="cuda") >= split)[:, None], w2.float()[None], w1.float()[None])
+        return n * w
+
+    ref = _attn_ref(rms(x[0], qw, qw2), rms(x[1], kw, kw2), x[2], None, None, cos, sin, D ** -0.5)
+    ref = ref.permute(0, 2, 1, 3).reshape(nseq * L, C)
+    r, _ = report(f"attn long L{L} D{D} impl{impl}", out, ref)
     assert r < 4e-3
 
 
