@@ -224,9 +224,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="osb200", choices=["osb200", "reference"])
-    ap.add_argument("--parallel", default="sp", choices=["sp", "dp"],
-                    help="N>1: sp = one sample sequence-sharded over ranks (strong scaling, north_star scheme); "
-                         "dp = one sample per rank (weak scaling, no collective)")
+    ap.add_argument("--parallel", default="dp", choices=["sp", "dp"],
+                    help="N>1: dp = one independent sample per rank, no data-path collective (weak scaling; the batch "
+                         "axis of north_star's 'batch x T' sharding); sp = ONE sample sequence-sharded over the ranks "
+                         "with all-to-all at the spatial<->temporal boundary (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vae", action="store_true", help="skip the VAE leg (encode/decode fps of BASELINE.json's metric)")
     args = ap.parse_args()

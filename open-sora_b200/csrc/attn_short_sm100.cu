@@ -438,48 +438,80 @@ __global__ void __launch_bounds__(kAttnThreads, (D <= 72) ? 2 : 1) attn_short_ke
 
 
 // ==========================================================================================================
-// Flash variant: warp-specialised, key blocks of BK <= 128 streamed through a 2-stage smem ring, online
-// softmax.  Roles (288 threads): warps 0-3 = softmax / O-correction / epilogue (one thread per query row),
-// warps 4-7 = loaders (norm + RoPE + transpose while staging Q and the K / V^T blocks), warp 8 = tcgen05
-// issuer.  All hand-offs are mbarriers; S (fp32) and P (bf16, written in place over S when kPTmem, else to a
-// swizzled smem tile) share one TMEM region, O accumulates in a second one and is rescaled in TMEM only when a
-// row maximum actually grows.  208 TMEM columns and ~100 KB smem at D=72 -> two CTAs per SM, so one CTA's
-// softmax overlaps the other's MMAs and loads.  No limit on the number of keys (MMDiT's 8828-token joint sequence).
+// Flash variant: warp-specialised, key blocks of BK <= 128, online softmax.  Roles (288 threads): warps 0-3 =
+// softmax / O-correction / epilogue (one thread per query row), warps 4-7 = loaders (RMSNorm + RoPE in fp32 while
+// staging Q, K and V into tensor-core operand tiles), warp 8 = tcgen05 issuer.  All hand-offs are mbarriers.
+//  * S (fp32) and P (bf16) share one TMEM region: P is written in place over S (kPTmem) and fed to the PV MMA as
+//    a tensor-memory A operand, or goes through a swizzled smem tile; O accumulates in a second TMEM region and is
+//    rescaled there only when a row maximum actually grows.
+//  * V is NOT transposed: it is staged row-major ([key][d], the same tile layout as K) and consumed as an
+//    MN-major B operand (64-wide main chunk 128B-swizzled, the 72->80 head-dim tail as a second N=16 MMA over a
+//    no-swizzle tile), so staging V costs ten 16-byte stores per key instead of 72 two-byte ones.
+//  * Key sets that fit the ring (<= 3 blocks: STDiT3 spatial / temporal / T5 cross) stay RESIDENT: they are staged
+//    once per CTA and reused by the QT query tiles of the work item; longer key sets (MMDiT's 8828-token joint
+//    sequence) stream through a 2-stage ring.
+//  208-240 TMEM columns and <= ~100 KB smem at D=72 -> two CTAs per SM: one CTA's softmax overlaps the other's
+//  staging and MMAs.
 // ==========================================================================================================
 constexpr int kFlashThreads = 288;
 
 struct FlashGeom {
-  int32_t BK, NKB;           // keys per block (multiple of 16, <= 128) and blocks per key set
-  int32_t k_bytes, kt_bytes, vt_bytes, p_bytes;  // per-stage smem sizes
-  int32_t off_qt, off_k, off_v, off_p, off_bar;
+  int32_t BK, NKB, NST;      // keys per block (multiple of 16, <= 128), blocks per key set, ring stages
+  int32_t resident;          // 1: NST == NKB, key blocks staged once per work item
+  int32_t QT, groups_per_seq; // q-tiles per work item (G == 1)
+  int32_t kv_stage_bytes, k_bytes, kt_bytes, v_bytes;  // per-stage smem sizes
+  int32_t off_qt, off_kv, off_p, off_bar;
   int32_t o_col, tmem_cols;
-  int64_t units;             // q-tile units (as in the resident kernel with QT = 1)
+  int64_t units;             // work units per head
   int64_t items;             // units * heads
 };
+
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;  // LBO: next 64-wide block along N
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                  // SBO: next group of 8 K-rows
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;                          // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ uint64_t make_noswz_mnmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(256 >> 4) << 16;  // LBO: next group of 8 K-rows
+  d |= static_cast<uint64_t>(128 >> 4) << 32;  // SBO: next 8-wide unit along N
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+// kind::f16 instruction descriptor with an MN-major B operand (bit 16)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_f32_bmn(uint32_t M, uint32_t N) {
+  return make_idesc_bf16_f32(M, N) | (1u << 16);
+}
 
 template <int D, bool kPTmem>
 __global__ void __launch_bounds__(kFlashThreads, (D <= 72) ? 2 : 1) attn_flash_kernel(const AttnParams p, const FlashGeom g) {
   using Cfg = AttnCfg<D>;
-  constexpr int DP = Cfg::DP, U = Cfg::U, UP = Cfg::UP;
+  constexpr int U = Cfg::U, UP = Cfg::UP;
+  constexpr int NMAIN = Cfg::MAIN * 64;   // O columns produced by the swizzled main chunk(s)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sQt = smem + g.off_qt;
-  auto sK = [&](int st) { return smem + g.off_k + st * (g.k_bytes + g.kt_bytes); };
-  auto sKt = [&](int st) { return smem + g.off_k + st * (g.k_bytes + g.kt_bytes) + g.k_bytes; };
-  auto sV = [&](int st) { return smem + g.off_v + st * g.vt_bytes; };
+  auto sK = [&](int st) { return smem + g.off_kv + st * g.kv_stage_bytes; };
+  auto sKt = [&](int st) { return smem + g.off_kv + st * g.kv_stage_bytes + g.k_bytes; };
+  auto sV = [&](int st) { return smem + g.off_kv + st * g.kv_stage_bytes + g.k_bytes + g.kt_bytes; };
+  auto sVt = [&](int st) { return smem + g.off_kv + st * g.kv_stage_bytes + g.k_bytes + g.kt_bytes + g.v_bytes; };
   uint8_t* sP = smem + g.off_p;
   const uint32_t bar0 = smem_u32(smem + g.off_bar);
   const uint32_t q_full = bar0, q_empty = bar0 + 8, s_full = bar0 + 16, p_full = bar0 + 24, o_full = bar0 + 32;
   auto kv_full = [&](int st) { return bar0 + 40 + 8 * st; };
-  auto kv_empty = [&](int st) { return bar0 + 56 + 8 * st; };
-  const uint32_t tmem_slot = bar0 + 72;
-  const int vt_chunk_bytes = DP * 128;
+  auto kv_empty = [&](int st) { return bar0 + 64 + 8 * st; };
+  const uint32_t tmem_slot = bar0 + 88;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   if (warp == 8) {
     if ((tid & 31) == 0) {
       mbar_init(q_full, 128); mbar_init(q_empty, 1); mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
-      for (int st = 0; st < 2; ++st) { mbar_init(kv_full(st), 128); mbar_init(kv_empty(st), 1); }
+      for (int st = 0; st < 3; ++st) { mbar_init(kv_full(st), 128); mbar_init(kv_empty(st), 1); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -491,12 +523,16 @@ __global__ void __launch_bounds__(kFlashThreads, (D <= 72) ? 2 : 1) attn_flash_k
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  // work item -> (unit, head): consecutive items share a head so concurrent CTAs reuse its K/V in L2
-  auto decode = [&](int64_t item, int64_t& seq0, int& tok0, int& h) {
+  // work item -> (sequence(s), q-tile range, head); consecutive items share a head (K/V of a head stay in L2)
+  auto decode = [&](int64_t item, int64_t& seq0, int& qt0, int& qt1, int& h) {
     h = (int)(item / g.units);
     const int64_t unit = item % g.units;
-    if (p.G > 1) { seq0 = unit * p.G; tok0 = 0; }
-    else { seq0 = unit / p.tiles_per_seq; tok0 = (int)(unit % p.tiles_per_seq) * 128; }
+    if (p.G > 1) { seq0 = unit * p.G; qt0 = 0; qt1 = 1; }
+    else {
+      seq0 = unit / g.groups_per_seq;
+      qt0 = (int)(unit % g.groups_per_seq) * g.QT;
+      qt1 = qt0 + g.QT < p.tiles_per_seq ? qt0 + g.QT : p.tiles_per_seq;
+    }
   };
 
   if (warp < 4) {
@@ -505,247 +541,260 @@ __global__ void __launch_bounds__(kFlashThreads, (D <= 72) ? 2 : 1) attn_flash_k
     const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
     uint32_t n_s = 0, n_o = 0;   // completed waits on s_full / o_full (parity = count & 1)
     for (int64_t item = blockIdx.x; item < g.items; item += gridDim.x) {
-      int64_t seq0; int tok0, h;
-      decode(item, seq0, tok0, h);
-      const int grp = (p.G > 1) ? r / p.Lq : 0;
-      const int qtok = (p.G > 1) ? r - grp * p.Lq : tok0 + r;
-      const int64_t qseq = seq0 + grp;
-      const bool q_valid = (grp < p.G) && (qseq < p.num_seqs) && (qtok < p.Lq);
-      int64_t q_row = 0;
-      int key_lo = 0x7fffffff, key_hi = 0;
-      if (q_valid) {
-        const int64_t b = qseq / p.seqs_per_batch, j = qseq % p.seqs_per_batch;
-        q_row = b * p.q_bs + j * p.q_ss + (int64_t)qtok * p.q_ts;
-        const int len = p.kv_lens ? p.kv_lens[qseq] : p.Lk;
-        key_lo = grp * p.Lk;
-        key_hi = key_lo + (len < p.Lk ? len : p.Lk);
-      }
-      float m = -INFINITY, l = 0.f;
-      for (int jb = 0; jb < g.NKB; ++jb) {
-        const int k0 = jb * g.BK;  // first key slot of this block
-        mbar_wait(s_full, n_s & 1); ++n_s;
-        tc_fence_after();
-        // ---- block maximum over this row's valid keys ----
-        float mb = -INFINITY;
-        for (int c0 = 0; c0 < g.BK; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_row + c0, v);
-          tmem_ld_wait();
-          const int ka = k0 + c0;
-          if (ka >= key_lo && ka + 32 <= key_hi && c0 + 32 <= g.BK) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) mb = fmaxf(mb, __uint_as_float(v[j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (ka + j >= key_lo && ka + j < key_hi && c0 + j < g.BK) mb = fmaxf(mb, __uint_as_float(v[j]));
-          }
-        }
-        const float m_new = fmaxf(m, mb);
-        const float ms = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
-        // ---- rescale the running O / l when this row's maximum grew (needs the previous PV finished) ----
-        if (jb > 0) {
-          mbar_wait(o_full, n_o & 1); ++n_o;
-          tc_fence_after();
-          const float alpha = (m == -INFINITY) ? 1.f : exp2f(m * p.scale_log2 - ms);
-          if (__any_sync(0xffffffffu, alpha != 1.f)) {
-#pragma unroll 1
-            for (int c = 0; c < DP; c += 8) {
-              uint32_t o[8];
-              tmem_ld_32x32b_x8(t_row + g.o_col + c, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int e = 0; e < 8; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-              tmem_st_32x32b_x8(t_row + g.o_col + c, o);
-            }
-            tmem_st_wait();
-          }
-          l *= alpha;
-        }
-        // ---- P = exp2(S*scale - max), row sum, store P (bf16) ----
-        for (int c0 = 0; c0 < g.BK; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_row + c0, v);
-          tmem_ld_wait();
-          float pr[32];
-          const int ka = k0 + c0;
-          if (ka >= key_lo && ka + 32 <= key_hi && c0 + 32 <= g.BK) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { pr[j] = exp2f(__uint_as_float(v[j]) * p.scale_log2 - ms); l += pr[j]; }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const bool ok = ka + j >= key_lo && ka + j < key_hi && c0 + j < g.BK;
-              pr[j] = ok ? exp2f(__uint_as_float(v[j]) * p.scale_log2 - ms) : 0.f;
-              l += pr[j];
-            }
-          }
-          if constexpr (kPTmem) {
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(pr[2 * j], pr[2 * j + 1]);
-            tmem_st_32x32b_x16(t_row + (c0 >> 1), pk);   // in place: P columns trail the S columns already read
-          } else {
-#pragma unroll
-            for (int u4 = 0; u4 < 4; ++u4) {
-              const int u = (c0 >> 3) + u4;
-              *reinterpret_cast<uint4*>(sP + (u >> 3) * (128 * 128) + sw128_off(r, u & 7)) = pack8(pr + u4 * 8);
-            }
-          }
-        }
-        m = m_new;
-        if constexpr (kPTmem) tmem_st_wait(); else fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(p_full);
-      }
-      // ---- epilogue: wait for the last PV, normalise, store ----
-      mbar_wait(o_full, n_o & 1); ++n_o;
-      tc_fence_after();
-      const float inv = l > 0.f ? 1.0f / l : 0.f;
-      __nv_bfloat16* orow = p.out + q_row * p.out_ld + (int64_t)h * D;
-#pragma unroll 1
-      for (int u = 0; u < U; ++u) {
-        uint32_t v[8];
-        tmem_ld_32x32b_x8(t_row + g.o_col + u * 8, v);
-        tmem_ld_wait();
-        if (q_valid) {
-          float o[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[e]) * inv;
-          *reinterpret_cast<uint4*>(orow + u * 8) = pack8(o);
-        }
-      }
-      tc_fence_before();  // O / S regions are overwritten by the next item's MMAs only after our p_full arrivals
-    }
-  } else if (warp < 8) {
-    // ============================ loaders: Q once per item, K / V^T per key block ============================
-    const int lt = tid - 128;
-    uint32_t n_q = 0, n_kv[2] = {0, 0};
-    for (int64_t item = blockIdx.x; item < g.items; item += gridDim.x) {
-      int64_t seq0; int tok0, h;
-      decode(item, seq0, tok0, h);
-      {  // ---- Q row `lt` ----
-        const int grp = (p.G > 1) ? lt / p.Lq : 0;
-        const int qtok = (p.G > 1) ? lt - grp * p.Lq : tok0 + lt;
+      int64_t seq0; int qt0, qt1, h;
+      decode(item, seq0, qt0, qt1, h);
+      for (int qt = qt0; qt < qt1; ++qt) {
+        const int grp = (p.G > 1) ? r / p.Lq : 0;
+        const int qtok = (p.G > 1) ? r - grp * p.Lq : qt * 128 + r;
         const int64_t qseq = seq0 + grp;
         const bool q_valid = (grp < p.G) && (qseq < p.num_seqs) && (qtok < p.Lq);
-        uint4 t[UP];
-#pragma unroll
-        for (int u = 0; u < U; ++u) t[u] = make_uint4(0, 0, 0, 0);
+        int64_t q_row = 0;
+        int key_lo = 0x7fffffff, key_hi = 0;
         if (q_valid) {
           const int64_t b = qseq / p.seqs_per_batch, j = qseq % p.seqs_per_batch;
-          const int64_t q_row = b * p.q_bs + j * p.q_ss + (int64_t)qtok * p.q_ts;
-          const uint4* qs = reinterpret_cast<const uint4*>(p.q + q_row * p.q_ld + (int64_t)h * D);
-#pragma unroll
-          for (int u = 0; u < U; ++u) t[u] = __ldg(qs + u);
+          q_row = b * p.q_bs + j * p.q_ss + (int64_t)qtok * p.q_ts;
+          const int len = p.kv_lens ? p.kv_lens[qseq] : p.Lk;
+          key_lo = grp * p.Lk;
+          key_hi = key_lo + (len < p.Lk ? len : p.Lk);
         }
-        float rq = 1.f;
-        if (p.qw != nullptr) {
-          float ss = 0.f;
+        float m = -INFINITY, l = 0.f;
+        for (int jb = 0; jb < g.NKB; ++jb) {
+          const int k0 = jb * g.BK;  // first key slot of this block
+          mbar_wait(s_full, n_s & 1); ++n_s;
+          tc_fence_after();
+          // ---- block maximum over this row's valid keys ----
+          float mb = -INFINITY;
+          for (int c0 = 0; c0 < g.BK; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_row + c0, v);
+            tmem_ld_wait();
+            const int ka = k0 + c0;
+            if (ka >= key_lo && ka + 32 <= key_hi && c0 + 32 <= g.BK) {
 #pragma unroll
-          for (int u = 0; u < U; ++u) ss += sumsq8(t[u]);
-          rq = rsqrtf(ss * (1.0f / D) + p.eps);
-        }
-        const __nv_bfloat16* qwt = (p.qw2 != nullptr && qtok >= p.norm_split) ? p.qw2 : p.qw;
-        mbar_wait(q_empty, (n_q & 1) ^ 1);   // previous item's S MMAs are done with sQ
-        finish_and_store_units<D, 0, UP>(t, rq, qwt, p.cos ? p.cos + (int64_t)qtok * (D / 2) : nullptr,
-                                         p.sin ? p.sin + (int64_t)qtok * (D / 2) : nullptr, sQ, 128 * 128, sQt, lt);
-        fence_proxy_async_smem();
-        mbar_arrive(q_full);
-        ++n_q;
-      }
-      for (int jb = 0; jb < g.NKB; ++jb) {
-        const int st = jb & 1;
-        // K/V slot handled by this thread inside block jb (BK <= 128 keys: one slot per loader thread)
-        const int slot = jb * g.BK + lt;
-        const bool in_blk = lt < g.BK;
-        const int kg = slot / p.Lk, ktok = slot - kg * p.Lk;
-        const int64_t kseq = seq0 + kg;
-        const bool k_valid = in_blk && (slot < p.NK) && (kseq < p.num_seqs);
-        uint4 tk[UP], tv[U];
+              for (int j = 0; j < 32; ++j) mb = fmaxf(mb, __uint_as_float(v[j]));
+            } else {
 #pragma unroll
-        for (int u = 0; u < U; ++u) { tk[u] = make_uint4(0, 0, 0, 0); tv[u] = make_uint4(0, 0, 0, 0); }
-        if (k_valid) {
-          const int64_t b = kseq / p.seqs_per_batch, j = kseq % p.seqs_per_batch;
-          const int64_t k_row = b * p.k_bs + j * p.k_ss + (int64_t)ktok * p.k_ts;
-          const uint4* ks = reinterpret_cast<const uint4*>(p.k + k_row * p.k_ld + (int64_t)h * D);
-          const uint4* vs = reinterpret_cast<const uint4*>(p.v + k_row * p.v_ld + (int64_t)h * D);
-#pragma unroll
-          for (int u = 0; u < U; ++u) tk[u] = __ldg(ks + u);
-#pragma unroll
-          for (int u = 0; u < U; ++u) tv[u] = __ldg(vs + u);
-        }
-        float rk = 1.f;
-        if (p.kw != nullptr) {
-          float ss = 0.f;
-#pragma unroll
-          for (int u = 0; u < U; ++u) ss += sumsq8(tk[u]);
-          rk = rsqrtf(ss * (1.0f / D) + p.eps);
-        }
-        mbar_wait(kv_empty(st), (n_kv[st] & 1) ^ 1);   // the PV MMA that read this stage two blocks ago is done
-        if (in_blk) {
-          const __nv_bfloat16* kwt = (p.kw2 != nullptr && ktok >= p.norm_split) ? p.kw2 : p.kw;
-          finish_and_store_units<D, 0, UP>(tk, rk, kwt, p.cos ? p.cos + (int64_t)ktok * (D / 2) : nullptr,
-                                           p.sin ? p.sin + (int64_t)ktok * (D / 2) : nullptr, sK(st), g.BK * 128, sKt(st), lt);
-          uint8_t* vt = sV(st) + (lt >> 6) * vt_chunk_bytes + (lt & 7) * 2;
-          const int ku = (lt & 63) >> 3;
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const uint32_t tw[4] = {tv[u].x, tv[u].y, tv[u].z, tv[u].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              *reinterpret_cast<uint16_t*>(vt + sw128_off(u * 8 + 2 * e, ku)) = (uint16_t)(tw[e] & 0xffffu);
-              *reinterpret_cast<uint16_t*>(vt + sw128_off(u * 8 + 2 * e + 1, ku)) = (uint16_t)(tw[e] >> 16);
+              for (int j = 0; j < 32; ++j)
+                if (ka + j >= key_lo && ka + j < key_hi && c0 + j < g.BK) mb = fmaxf(mb, __uint_as_float(v[j]));
             }
           }
+          const float m_new = fmaxf(m, mb);
+          const float ms = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
+          // ---- rescale the running O / l when this row's maximum grew (needs the previous PV finished) ----
+          if (jb > 0) {
+            mbar_wait(o_full, n_o & 1); ++n_o;
+            tc_fence_after();
+            const float alpha = (m == -INFINITY) ? 1.f : exp2f(m * p.scale_log2 - ms);
+            if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll 1
+              for (int c = 0; c < Cfg::DP; c += 8) {
+                uint32_t o[8];
+                tmem_ld_32x32b_x8(t_row + g.o_col + c, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                tmem_st_32x32b_x8(t_row + g.o_col + c, o);
+              }
+              tmem_st_wait();
+            }
+            l *= alpha;
+          }
+          // ---- P = exp2(S*scale - max), row sum, store P (bf16) ----
+          for (int c0 = 0; c0 < g.BK; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_row + c0, v);
+            tmem_ld_wait();
+            float pr[32];
+            const int ka = k0 + c0;
+            if (ka >= key_lo && ka + 32 <= key_hi && c0 + 32 <= g.BK) {
+              float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;  // four chains: the adds do not serialise
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                pr[j] = exp2f(__uint_as_float(v[j]) * p.scale_log2 - ms); l0 += pr[j];
+                pr[j + 1] = exp2f(__uint_as_float(v[j + 1]) * p.scale_log2 - ms); l1 += pr[j + 1];
+                pr[j + 2] = exp2f(__uint_as_float(v[j + 2]) * p.scale_log2 - ms); l2 += pr[j + 2];
+                pr[j + 3] = exp2f(__uint_as_float(v[j + 3]) * p.scale_log2 - ms); l3 += pr[j + 3];
+              }
+              l += (l0 + l1) + (l2 + l3);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const bool ok = ka + j >= key_lo && ka + j < key_hi && c0 + j < g.BK;
+                pr[j] = ok ? exp2f(__uint_as_float(v[j]) * p.scale_log2 - ms) : 0.f;
+                l += pr[j];
+              }
+            }
+            if constexpr (kPTmem) {
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(pr[2 * j], pr[2 * j + 1]);
+              tmem_st_32x32b_x16(t_row + (c0 >> 1), pk);   // in place: P columns trail the S columns already read
+            } else {
+#pragma unroll
+              for (int u4 = 0; u4 < 4; ++u4) {
+                const int u = (c0 >> 3) + u4;
+                *reinterpret_cast<uint4*>(sP + (u >> 3) * (128 * 128) + sw128_off(r, u & 7)) = pack8(pr + u4 * 8);
+              }
+            }
+          }
+          m = m_new;
+          if constexpr (kPTmem) tmem_st_wait(); else fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(p_full);
         }
-        fence_proxy_async_smem();
-        mbar_arrive(kv_full(st));
-        ++n_kv[st];
+        // ---- epilogue: wait for the last PV, normalise, store ----
+        mbar_wait(o_full, n_o & 1); ++n_o;
+        tc_fence_after();
+        const float inv = l > 0.f ? 1.0f / l : 0.f;
+        __nv_bfloat16* orow = p.out + q_row * p.out_ld + (int64_t)h * D;
+#pragma unroll 1
+        for (int u = 0; u < U; ++u) {
+          uint32_t v[8];
+          tmem_ld_32x32b_x8(t_row + g.o_col + u * 8, v);
+          tmem_ld_wait();
+          if (q_valid) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[e]) * inv;
+            *reinterpret_cast<uint4*>(orow + u * 8) = pack8(o);
+          }
+        }
+        tc_fence_before();  // O / S regions are overwritten by later MMAs only after our next p_full arrivals
+      }
+    }
+  } else if (warp < 8) {
+    // ============================ loaders: Q per q-tile, K / V per key block (once per item when resident) ======
+    const int lt = tid - 128;
+    uint32_t n_q = 0, n_kv[3] = {0, 0, 0};
+    for (int64_t item = blockIdx.x; item < g.items; item += gridDim.x) {
+      int64_t seq0; int qt0, qt1, h;
+      decode(item, seq0, qt0, qt1, h);
+      for (int qt = qt0; qt < qt1; ++qt) {
+        {  // ---- Q row `lt` of q-tile qt ----
+          const int grp = (p.G > 1) ? lt / p.Lq : 0;
+          const int qtok = (p.G > 1) ? lt - grp * p.Lq : qt * 128 + lt;
+          const int64_t qseq = seq0 + grp;
+          const bool q_valid = (grp < p.G) && (qseq < p.num_seqs) && (qtok < p.Lq);
+          uint4 t[UP];
+#pragma unroll
+          for (int u = 0; u < U; ++u) t[u] = make_uint4(0, 0, 0, 0);
+          if (q_valid) {
+            const int64_t b = qseq / p.seqs_per_batch, j = qseq % p.seqs_per_batch;
+            const int64_t q_row = b * p.q_bs + j * p.q_ss + (int64_t)qtok * p.q_ts;
+            const uint4* qs = reinterpret_cast<const uint4*>(p.q + q_row * p.q_ld + (int64_t)h * D);
+#pragma unroll
+            for (int u = 0; u < U; ++u) t[u] = __ldg(qs + u);
+          }
+          float rq = 1.f;
+          if (p.qw != nullptr) {
+            float ss = 0.f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) ss += sumsq8(t[u]);
+            rq = rsqrtf(ss * (1.0f / D) + p.eps);
+          }
+          const __nv_bfloat16* qwt = (p.qw2 != nullptr && qtok >= p.norm_split) ? p.qw2 : p.qw;
+          mbar_wait(q_empty, (n_q & 1) ^ 1);   // the previous q-tile's S MMAs are done with sQ
+          finish_and_store_units<D, 0, UP>(t, rq, qwt, p.cos ? p.cos + (int64_t)qtok * (D / 2) : nullptr,
+                                           p.sin ? p.sin + (int64_t)qtok * (D / 2) : nullptr, sQ, 128 * 128, sQt, lt);
+          fence_proxy_async_smem();
+          mbar_arrive(q_full);
+          ++n_q;
+        }
+        if (g.resident && qt != qt0) continue;   // key blocks of this item are already in the ring
+        for (int jb = 0; jb < g.NKB; ++jb) {
+          const int st = g.resident ? jb : (jb & 1);
+          // K/V slot handled by this thread inside block jb (BK <= 128 keys: one slot per loader thread)
+          const int slot = jb * g.BK + lt;
+          const bool in_blk = lt < g.BK;
+          const int kg = slot / p.Lk, ktok = slot - kg * p.Lk;
+          const int64_t kseq = seq0 + kg;
+          const bool k_valid = in_blk && (slot < p.NK) && (kseq < p.num_seqs);
+          uint4 tk[UP], tv[UP];
+#pragma unroll
+          for (int u = 0; u < U; ++u) { tk[u] = make_uint4(0, 0, 0, 0); tv[u] = make_uint4(0, 0, 0, 0); }
+          if (k_valid) {
+            const int64_t b = kseq / p.seqs_per_batch, j = kseq % p.seqs_per_batch;
+            const int64_t k_row = b * p.k_bs + j * p.k_ss + (int64_t)ktok * p.k_ts;
+            const uint4* ks = reinterpret_cast<const uint4*>(p.k + k_row * p.k_ld + (int64_t)h * D);
+            const uint4* vs = reinterpret_cast<const uint4*>(p.v + k_row * p.v_ld + (int64_t)h * D);
+#pragma unroll
+            for (int u = 0; u < U; ++u) tk[u] = __ldg(ks + u);
+#pragma unroll
+            for (int u = 0; u < U; ++u) tv[u] = __ldg(vs + u);
+          }
+          float rk = 1.f;
+          if (p.kw != nullptr) {
+            float ss = 0.f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) ss += sumsq8(tk[u]);
+            rk = rsqrtf(ss * (1.0f / D) + p.eps);
+          }
+          mbar_wait(kv_empty(st), (n_kv[st] & 1) ^ 1);   // every MMA that read this stage before has completed
+          if (in_blk) {
+            const __nv_bfloat16* kwt = (p.kw2 != nullptr && ktok >= p.norm_split) ? p.kw2 : p.kw;
+            finish_and_store_units<D, 0, UP>(tk, rk, kwt, p.cos ? p.cos + (int64_t)ktok * (D / 2) : nullptr,
+                                             p.sin ? p.sin + (int64_t)ktok * (D / 2) : nullptr, sK(st), g.BK * 128, sKt(st), lt);
+            // V keeps its [key][d] orientation (MN-major B operand): same tile layout as K, no arithmetic
+            finish_and_store_units<D, 0, UP>(tv, 1.f, nullptr, nullptr, nullptr, sV(st), g.BK * 128, sVt(st), lt);
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(kv_full(st));
+          ++n_kv[st];
+        }
       }
     }
   } else {
     // ============================ tcgen05 issuer ============================
     if ((tid & 31) == 0) {
-      uint32_t n_q = 0, n_p = 0, n_kv[2] = {0, 0};
+      uint32_t n_q = 0, n_p = 0, n_kv[3] = {0, 0, 0};
       const uint32_t idesc_s = make_idesc_bf16_f32(128, g.BK);
-      const uint32_t idesc_o = make_idesc_bf16_f32(128, DP);
+      const uint32_t idesc_om = make_idesc_bf16_f32_bmn(128, NMAIN);
+      const uint32_t idesc_ot = make_idesc_bf16_f32_bmn(128, 16);
       for (int64_t item = blockIdx.x; item < g.items; item += gridDim.x) {
-        mbar_wait(q_full, n_q & 1); ++n_q;
-        for (int jb = 0; jb < g.NKB; ++jb) {
-          const int st = jb & 1;
-          mbar_wait(kv_full(st), n_kv[st] & 1); ++n_kv[st];
-          tc_fence_after();
-          // S = Q K^T  (overwrites the S/P region: ordered after the previous PV by the in-order MMA pipe)
-          uint32_t acc = 0;
+        int64_t seq0; int qt0, qt1, h;
+        decode(item, seq0, qt0, qt1, h);
+        for (int qt = qt0; qt < qt1; ++qt) {
+          mbar_wait(q_full, n_q & 1); ++n_q;
+          for (int jb = 0; jb < g.NKB; ++jb) {
+            const int st = g.resident ? jb : (jb & 1);
+            if (!g.resident || qt == qt0) { mbar_wait(kv_full(st), n_kv[st] & 1); ++n_kv[st]; }
+            tc_fence_after();
+            // S = Q K^T  (overwrites the S/P region: ordered after the previous PV by the in-order MMA pipe)
+            uint32_t acc = 0;
 #pragma unroll
-          for (int kc = 0; kc < Cfg::MAIN; ++kc) {
+            for (int kc = 0; kc < Cfg::MAIN; ++kc) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              umma_bf16<1>(tmem_base, make_sw128_kmajor_desc(smem_u32(sQ) + kc * (128 * 128) + ks * 32),
-                           make_sw128_kmajor_desc(smem_u32(sK(st)) + kc * (g.BK * 128) + ks * 32), idesc_s, acc);
-              acc = 1;
+              for (int ks = 0; ks < 4; ++ks) {
+                umma_bf16<1>(tmem_base, make_sw128_kmajor_desc(smem_u32(sQ) + kc * (128 * 128) + ks * 32),
+                             make_sw128_kmajor_desc(smem_u32(sK(st)) + kc * (g.BK * 128) + ks * 32), idesc_s, acc);
+                acc = 1;
+              }
             }
-          }
-          if (Cfg::TAIL)
-            umma_bf16<1>(tmem_base, make_noswz_kmajor_desc(smem_u32(sQt)), make_noswz_kmajor_desc(smem_u32(sKt(st))), idesc_s, acc);
-          umma_commit<1>(s_full);
-          if (jb == g.NKB - 1) umma_commit<1>(q_empty);   // sQ may be restaged for the next item
-          mbar_wait(p_full, n_p & 1); ++n_p;
-          tc_fence_after();
-          // O (+)= P V
-          const int steps = g.BK / 16;
-          for (int s = 0; s < steps; ++s) {
-            const uint64_t db = make_sw128_kmajor_desc(smem_u32(sV(st)) + (s >> 2) * vt_chunk_bytes + (s & 3) * 32);
-            if constexpr (kPTmem) {
-              umma_bf16_ts(tmem_base + g.o_col, tmem_base + s * 8, db, idesc_o, (jb > 0 || s > 0) ? 1u : 0u);
-            } else {
-              umma_bf16<1>(tmem_base + g.o_col, make_sw128_kmajor_desc(smem_u32(sP) + (s >> 2) * (128 * 128) + (s & 3) * 32),
-                           db, idesc_o, (jb > 0 || s > 0) ? 1u : 0u);
+            if (Cfg::TAIL)
+              umma_bf16<1>(tmem_base, make_noswz_kmajor_desc(smem_u32(sQt)), make_noswz_kmajor_desc(smem_u32(sKt(st))), idesc_s, acc);
+            umma_commit<1>(s_full);
+            if (jb == g.NKB - 1) umma_commit<1>(q_empty);   // sQ may be restaged for the next q-tile
+            mbar_wait(p_full, n_p & 1); ++n_p;
+            tc_fence_after();
+            // O (+)= P V : per 16 keys, one MMA over the swizzled main chunk(s) (N = 64 / 128) and one over the
+            // no-swizzle head-dim tail (N = 16); V is read as an MN-major operand (no transposition anywhere)
+            const int steps = g.BK / 16;
+            for (int s = 0; s < steps; ++s) {
+              const uint32_t accu = (jb > 0 || s > 0) ? 1u : 0u;
+              const uint64_t dbm = make_sw128_mnmajor_desc(smem_u32(sV(st)) + s * 2048, (uint32_t)(g.BK * 128));
+              const uint64_t dbt = make_noswz_mnmajor_desc(smem_u32(sVt(st)) + s * 512);
+              if constexpr (kPTmem) {
+                umma_bf16_ts(tmem_base + g.o_col, tmem_base + s * 8, dbm, idesc_om, accu);
+                if (Cfg::TAIL) umma_bf16_ts(tmem_base + g.o_col + NMAIN, tmem_base + s * 8, dbt, idesc_ot, accu);
+              } else {
+                const uint64_t da = make_sw128_kmajor_desc(smem_u32(sP) + (s >> 2) * (128 * 128) + (s & 3) * 32);
+                umma_bf16<1>(tmem_base + g.o_col, da, dbm, idesc_om, accu);
+                if (Cfg::TAIL) umma_bf16<1>(tmem_base + g.o_col + NMAIN, da, dbt, idesc_ot, accu);
+              }
             }
+            if (!g.resident || qt == qt1 - 1) umma_commit<1>(kv_empty(st));   // stage free once its last reader is done
+            umma_commit<1>(o_full);
           }
-          umma_commit<1>(kv_empty(st));
-          umma_commit<1>(o_full);
         }
       }
     }
@@ -762,33 +811,52 @@ __global__ void __launch_bounds__(kFlashThreads, (D <= 72) ? 2 : 1) attn_flash_k
 template <int D, bool kPTmem>
 static int attn_flash_launch(AttnParams& p, int H, cudaStream_t stream) {
   using Cfg = AttnCfg<D>;
-  FlashGeom g;
+  FlashGeom g = {};
   auto up1k = [](int x) { return (x + 1023) / 1024 * 1024; };
-  // q-tile units exactly as the resident kernel with one q-tile per unit
-  if (p.G > 1) g.units = (p.num_seqs + p.G - 1) / p.G;
-  else g.units = p.num_seqs * p.tiles_per_seq;
-  g.items = g.units * H;
   g.NKB = (p.NK + 127) / 128;
   g.BK = (((p.NK + g.NKB - 1) / g.NKB) + 15) / 16 * 16;
   const int nkc = (g.BK + 63) / 64;
   g.k_bytes = up1k(Cfg::MAIN * g.BK * 128);
   g.kt_bytes = up1k(Cfg::TAIL ? g.BK * 32 : 0);
-  g.vt_bytes = nkc * Cfg::DP * 128;
-  g.p_bytes = kPTmem ? 0 : nkc * 128 * 128;
+  g.v_bytes = g.k_bytes;
+  g.kv_stage_bytes = 2 * (g.k_bytes + g.kt_bytes);
+  g.resident = (g.NKB <= 3) ? 1 : 0;
+  g.NST = g.resident ? g.NKB : 2;
+  const int p_bytes = kPTmem ? 0 : nkc * 128 * 128;
   int off = Cfg::MAIN * 128 * 128;
   g.off_qt = off; off += up1k(Cfg::TAIL ? 128 * 32 : 0);
-  g.off_k = off; off += 2 * (g.k_bytes + g.kt_bytes);
-  g.off_v = off; off += up1k(2 * g.vt_bytes);
-  g.off_p = off; off += g.p_bytes;
+  g.off_kv = off; off += g.NST * g.kv_stage_bytes;
+  g.off_p = off; off += p_bytes;
   g.off_bar = off; off += 128;
   const int smem = off;
   const int s_cols = (g.BK + 31) / 32 * 32;
   g.o_col = s_cols;
   g.tmem_cols = (s_cols + Cfg::DP <= 256) ? 256 : 512;
   if (smem > 227 * 1024) { set_error("osb_attn_short(flash): %d B smem", smem); return OSB_ERR_UNSUPPORTED; }
-  const int per_sm = (D <= 72 && smem <= 110 * 1024 && g.tmem_cols == 256) ? 2 : 1;
-  int64_t grid = (int64_t)sm_count() * per_sm;
-  if (grid > g.items) grid = g.items;
+  const int per_sm = (D <= 72 && smem <= 112 * 1024 && g.tmem_cols == 256) ? 2 : 1;
+  const int64_t slots = (int64_t)sm_count() * per_sm;
+  // work units: q-tiles grouped QT at a time when the key set is resident (amortises its staging)
+  g.QT = 1;
+  g.groups_per_seq = p.tiles_per_seq;
+  if (p.G > 1) {
+    g.units = (p.num_seqs + p.G - 1) / p.G;
+  } else {
+    if (g.resident) {
+      const double staging = 0.7 * g.NKB;  // staging one key block ~ 0.7 q-tile-blocks of softmax work
+      double best = 1e30;
+      for (int cand = 1; cand <= p.tiles_per_seq && cand <= 64; ++cand) {
+        const int64_t groups = (p.tiles_per_seq + cand - 1) / cand;
+        const int64_t ctas = p.num_seqs * groups * H;
+        const int64_t waves = (ctas + slots - 1) / slots;
+        const double cost = (double)waves * ((double)((p.tiles_per_seq + groups - 1) / groups) * g.NKB + staging);
+        if (cost < best - 1e-9) { best = cost; g.QT = cand; }
+      }
+      g.groups_per_seq = (p.tiles_per_seq + g.QT - 1) / g.QT;
+    }
+    g.units = p.num_seqs * g.groups_per_seq;
+  }
+  g.items = g.units * H;
+  int64_t grid = slots < g.items ? slots : g.items;
   attn_flash_kernel<D, kPTmem><<<(unsigned)grid, kFlashThreads, smem, stream>>>(p, g);
   OSB_CHECK_CUDA(cudaGetLastError());
   count_launch();
