@@ -22,7 +22,6 @@ namespace osb {
 
 constexpr int kAttnThreads = 256;
 constexpr int kMaxKeys = 320;  // padded keys per tile (resident kernel)
-constexpr int kDefaultAttnImpl = 1;  // 1 resident, 2 flash/smem-P, 3 flash/TMEM-P (see osb_attn_short)
 
 struct AttnParams {
   const __nv_bfloat16* q; const __nv_bfloat16* k; const __nv_bfloat16* v; __nv_bfloat16* out;
@@ -36,6 +35,7 @@ struct AttnParams {
   int32_t norm_split;
   float eps;
   const float* cos; const float* sin;
+  int32_t rope_half;     // 1: rotate-half pairing (i, i + D/2) (HF / Liger layout), 0: interleaved pairs (2i, 2i+1)
   float scale_log2;      // softmax_scale * log2(e)
   int32_t G;             // sequences packed per tile (1 when Lq >= 128)
   int32_t tiles_per_seq; // q-tiles per sequence (G == 1)
@@ -138,6 +138,48 @@ __device__ __forceinline__ void finish_and_store_units(const uint4* raw, float r
     else
       *reinterpret_cast<uint4*>(tail_base + tail_off(row, u - Cfg::MAIN * 8)) = o;
   }
+}
+
+// Full head row with rotate-half RoPE (LigerRopeFunction, math.py:27): element i pairs with i + D/2, so units u and
+// u + U/2 are processed together: x1' = x1 cos_i - x2 sin_i, x2' = x2 cos_i + x1 sin_i.
+template <int D>
+__device__ __forceinline__ void finish_and_store_row_half(const uint4* raw, float r, const __nv_bfloat16* w, const float* cosr,
+                                                          const float* sinr, uint8_t* main_base, int main_chunk_bytes,
+                                                          uint8_t* tail_base, int row) {
+  using Cfg = AttnCfg<D>;
+  constexpr int U = Cfg::U, HU = U / 2;
+  static_assert(U % 2 == 0 || true, "rotate-half needs an even number of 16-byte units");
+#pragma unroll
+  for (int u = 0; u < HU; ++u) {
+    float x1[8], x2[8];
+    unpack8(raw[u], x1);
+    unpack8(raw[u + HU], x2);
+    if (w != nullptr) {
+      float w1[8], w2[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(w) + u), w1);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(w) + u + HU), w2);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { x1[e] *= r * w1[e]; x2[e] *= r * w2[e]; }
+    }
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(cosr) + 2 * u), c1 = __ldg(reinterpret_cast<const float4*>(cosr) + 2 * u + 1);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(sinr) + 2 * u), s1 = __ldg(reinterpret_cast<const float4*>(sinr) + 2 * u + 1);
+    const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w}, ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float a = x1[e], b = x2[e];
+      x1[e] = a * cc[e] - b * ss[e];
+      x2[e] = b * cc[e] + a * ss[e];
+    }
+    const uint4 o1 = pack8(x1), o2 = pack8(x2);
+    const int ua = u, ub = u + HU;
+    if (ua < Cfg::MAIN * 8) *reinterpret_cast<uint4*>(main_base + (ua >> 3) * main_chunk_bytes + sw128_off(row, ua & 7)) = o1;
+    else *reinterpret_cast<uint4*>(tail_base + tail_off(row, ua - Cfg::MAIN * 8)) = o1;
+    if (ub < Cfg::MAIN * 8) *reinterpret_cast<uint4*>(main_base + (ub >> 3) * main_chunk_bytes + sw128_off(row, ub & 7)) = o2;
+    else *reinterpret_cast<uint4*>(tail_base + tail_off(row, ub - Cfg::MAIN * 8)) = o2;
+  }
+#pragma unroll
+  for (int u = U; u < Cfg::UP; ++u)
+    *reinterpret_cast<uint4*>(tail_base + tail_off(row, u - Cfg::MAIN * 8)) = make_uint4(0, 0, 0, 0);
 }
 
 __device__ __forceinline__ float sumsq8(const uint4& t) {
@@ -694,8 +736,12 @@ __global__ void __launch_bounds__(kFlashThreads, (D <= 72) ? 2 : 1) attn_flash_k
           }
           const __nv_bfloat16* qwt = (p.qw2 != nullptr && qtok >= p.norm_split) ? p.qw2 : p.qw;
           mbar_wait(q_empty, (n_q & 1) ^ 1);   // the previous q-tile's S MMAs are done with sQ
-          finish_and_store_units<D, 0, UP>(t, rq, qwt, p.cos ? p.cos + (int64_t)qtok * (D / 2) : nullptr,
-                                           p.sin ? p.sin + (int64_t)qtok * (D / 2) : nullptr, sQ, 128 * 128, sQt, lt);
+          if ((U % 2 == 0) && p.rope_half)
+            finish_and_store_row_half<D>(t, rq, qwt, p.cos + (int64_t)qtok * (D / 2), p.sin + (int64_t)qtok * (D / 2), sQ,
+                                         128 * 128, sQt, lt);
+          else
+            finish_and_store_units<D, 0, UP>(t, rq, qwt, p.cos ? p.cos + (int64_t)qtok * (D / 2) : nullptr,
+                                             p.sin ? p.sin + (int64_t)qtok * (D / 2) : nullptr, sQ, 128 * 128, sQt, lt);
           fence_proxy_async_smem();
           mbar_arrive(q_full);
           ++n_q;
@@ -732,8 +778,12 @@ __global__ void __launch_bounds__(kFlashThreads, (D <= 72) ? 2 : 1) attn_flash_k
           mbar_wait(kv_empty(st), (n_kv[st] & 1) ^ 1);   // every MMA that read this stage before has completed
           if (in_blk) {
             const __nv_bfloat16* kwt = (p.kw2 != nullptr && ktok >= p.norm_split) ? p.kw2 : p.kw;
-            finish_and_store_units<D, 0, UP>(tk, rk, kwt, p.cos ? p.cos + (int64_t)ktok * (D / 2) : nullptr,
-                                             p.sin ? p.sin + (int64_t)ktok * (D / 2) : nullptr, sK(st), g.BK * 128, sKt(st), lt);
+            if ((U % 2 == 0) && p.rope_half)
+              finish_and_store_row_half<D>(tk, rk, kwt, p.cos + (int64_t)ktok * (D / 2), p.sin + (int64_t)ktok * (D / 2),
+                                           sK(st), g.BK * 128, sKt(st), lt);
+            else
+              finish_and_store_units<D, 0, UP>(tk, rk, kwt, p.cos ? p.cos + (int64_t)ktok * (D / 2) : nullptr,
+                                               p.sin ? p.sin + (int64_t)ktok * (D / 2) : nullptr, sK(st), g.BK * 128, sKt(st), lt);
             // V keeps its [key][d] orientation (MN-major B operand): same tile layout as K, no arithmetic
             finish_and_store_units<D, 0, UP>(tv, 1.f, nullptr, nullptr, nullptr, sV(st), g.BK * 128, sVt(st), lt);
           }
@@ -945,6 +995,8 @@ extern "C" int osb_attn_short(const osb_attn_short_args* a, void* stream) {
   p.norm_split = a->norm_split;
   p.eps = a->norm_eps;
   p.cos = a->rope_cos; p.sin = a->rope_sin;
+  p.rope_half = a->rope_cos != nullptr && a->rope_half ? 1 : 0;
+  OSB_REQUIRE(!p.rope_half || (D % 16 == 0), "osb_attn_short: rotate-half RoPE needs head_dim %% 16 == 0");
   p.scale_log2 = a->softmax_scale * 1.4426950408889634f;
   int64_t units;
   if (a->Lq >= 128) {
@@ -979,8 +1031,14 @@ extern "C" int osb_attn_short(const osb_attn_short_args* a, void* stream) {
   p.NKP = (p.NK + 15) / 16 * 16;
   // implementation: reserved = 1 resident-key kernel, 2 flash (P through smem), 3 flash (P in TMEM), 0 = default
   int impl = a->reserved;
-  if (impl == 0) impl = kDefaultAttnImpl;
-  if (p.NK > kMaxKeys && impl == 1) impl = kDefaultAttnImpl == 1 ? 2 : kDefaultAttnImpl;
+  if (impl == 0) {
+    // measured on B200 (profiles/r01_attn_v4.log): the flash kernel with P in TMEM wins when two key blocks are
+    // resident and two CTAs fit an SM (STDiT3 spatial: 128 vs 153 us); the one-pass resident kernel wins for a
+    // single block (temporal) and for 3 resident blocks at one CTA per SM (T5 cross: 117 vs 209 us)
+    const int nkb = (p.NK + 127) / 128;
+    impl = (p.NK > kMaxKeys) ? 3 : ((nkb == 2 && D <= 72) ? 3 : 1);
+  }
+  if ((p.NK > kMaxKeys || p.rope_half) && impl == 1) impl = 3;  // the resident kernel splits q rows between two threads
   if (impl == 2 || impl == 3) {
     cudaStream_t fs = static_cast<cudaStream_t>(stream);
     const int H = a->num_heads;

@@ -54,7 +54,7 @@ int make_tmap_5d_bf16(CUtensorMap* map, const void* base, const uint64_t dims[5]
 #ifdef __CUDACC__
 
 #ifndef OSB_SPIN_LIMIT
-#define OSB_SPIN_LIMIT (1u << 26)  // bounded waits: a protocol bug traps instead of hanging the box
+#define OSB_SPIN_LIMIT (1u << 24)  // bounded waits: a protocol bug traps instead of hanging the box
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -9,9 +9,8 @@ they read the block's own parameters and run every FLOP on libosb200 (sm_100a):
   `norm_split`); `linear2(cat(attn, gelu(mlp)))` reads ONE [rows, 5C] buffer that the attention kernel and the
   GELU GEMM wrote side by side (no torch.cat materialisation).
 
-Limits of this round: the joint sequence must fit the short-key attention kernel (L_txt + L_img <= 320 keys per
-sample; the streaming kernel for L = 8828 is the next kernel on SURVEY.md §8 row a-M) and RoPE must be the Flux
-interleaved layout (`EmbedND`); `LigerEmbedND`'s rotate-half layout raises NotImplementedError."""
+Any joint sequence length (the flash attention variant streams key blocks), both RoPE layouts (`EmbedND`
+interleaved pairs and `LigerEmbedND` rotate-half) and both QKV checkpoint layouts (`fused_qkv` True / False)."""
 from __future__ import annotations
 
 import math
@@ -164,11 +163,8 @@ def _check(x: Tensor):
 
 
 def _rope(pe):
-    cos, sin, half = rope_tables(pe)
-    if half:
-        raise NotImplementedError("rotate-half (LigerEmbedND) RoPE is not built into the osb200 attention kernel yet: "
-                                  "use use_liger_rope=False (math.py:60-65 interleaved layout)")
-    return cos, sin
+    """(cos, sin, rotate_half) for the attention kernel: EmbedND -> interleaved pairs, LigerEmbedND -> rotate-half."""
+    return rope_tables(pe)
 
 
 class DoubleStreamBlockProcessor:
@@ -191,13 +187,13 @@ class DoubleStreamBlockProcessor:
         for b in range(B):
             osb.gemm(xt[b * Lt:(b + 1) * Lt], wt, bt, out=qkv[b * L:b * L + Lt])
             osb.gemm(xi[b * Li:(b + 1) * Li], wi, bi, out=qkv[b * L + Lt:(b + 1) * L])
-        cos, sin = _rope(pe)
+        cos, sin, half = _rope(pe)
         ao = torch.empty(B * L, C, dtype=img.dtype, device=img.device)
         osb.attn_short(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], ao, num_seqs=B, seqs_per_batch=1, q_strides=(L, 0, 1),
                        k_strides=(L, 0, 1), Lq=L, Lk=L, num_heads=H, head_dim=D,
                        q_norm_w=attn.txt_attn.norm.query_norm.scale, k_norm_w=attn.txt_attn.norm.key_norm.scale,
                        q_norm_w2=attn.img_attn.norm.query_norm.scale, k_norm_w2=attn.img_attn.norm.key_norm.scale,
-                       norm_split=Lt, rope_cos=cos, rope_sin=sin)
+                       norm_split=Lt, rope_cos=cos, rope_sin=sin, rope_half=half)
         img_o, txt_o = torch.empty_like(img2), torch.empty_like(txt2)
         for b in range(B):  # x + gate * proj(attn)   (layers.py:247, 251)
             osb.gemm(ao[b * L + Lt:(b + 1) * L], attn.img_attn.proj.weight, attn.img_attn.proj.bias,
@@ -258,10 +254,11 @@ class SingleStreamBlockProcessor:
         qkv = osb.gemm(xm, wq, bq)                                               # [B*L, 3C]
         cat = torch.empty(B * L, C + M4, dtype=x.dtype, device=x.device)         # [attn | gelu(mlp)] side by side
         osb.gemm(xm, wm, bm, epilogue=osb.EPI_BIAS_GELU_TANH, out=cat[:, C:])
-        cos, sin = _rope(pe)
+        cos, sin, half = _rope(pe)
         osb.attn_short(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], cat[:, :C], num_seqs=B, seqs_per_batch=1,
                        q_strides=(L, 0, 1), k_strides=(L, 0, 1), Lq=L, Lk=L, num_heads=H, head_dim=D,
-                       q_norm_w=attn.norm.query_norm.scale, k_norm_w=attn.norm.key_norm.scale, rope_cos=cos, rope_sin=sin)
+                       q_norm_w=attn.norm.query_norm.scale, k_norm_w=attn.norm.key_norm.scale, rope_cos=cos, rope_sin=sin,
+                       rope_half=half)
         out = osb.gemm(cat, attn.linear2.weight, attn.linear2.bias, epilogue=osb.EPI_BIAS_GATE_RES, residual=x2,
                        gate=mod.gate, group_rows=L)
         return out.view(B, L, C)

@@ -133,6 +133,7 @@ class AttnShortArgs(C.Structure):
         ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
         ("softmax_scale", C.c_float),
         ("q_norm_w2", C.c_void_p), ("k_norm_w2", C.c_void_p), ("norm_split", C.c_int32), ("reserved", C.c_int32),
+        ("rope_half", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 
@@ -264,7 +265,7 @@ def gemm(a, w, bias=None, *, epilogue: int = EPI_BIAS, residual=None, gate=None,
 def attn_short(q, k, v, out, *, num_seqs: int, seqs_per_batch: int, q_strides, k_strides, Lq: int, Lk: int,
                num_heads: int, head_dim: int, kv_lens=None, q_norm_w=None, k_norm_w=None, norm_eps: float = 1e-6,
                rope_cos=None, rope_sin=None, softmax_scale: float | None = None, q_norm_w2=None, k_norm_w2=None,
-               norm_split: int = 0, impl: int = 0):
+               norm_split: int = 0, impl: int = 0, rope_half: bool = False):
     """softmax(q k^T * scale) v per (sequence, head) with optional fused QK-RMSNorm and RoPE.
     q/k/v/out are 2-D bf16 views [rows, ld]; *_strides = (batch, seq, token) strides in rows."""
     import torch
@@ -292,6 +293,7 @@ def attn_short(q, k, v, out, *, num_seqs: int, seqs_per_batch: int, q_strides, k
     a.q_norm_w2 = q_norm_w2.data_ptr() if q_norm_w2 is not None else None
     a.k_norm_w2 = k_norm_w2.data_ptr() if k_norm_w2 is not None else None
     a.norm_split = norm_split
+    a.rope_half = int(rope_half)
     a.reserved = impl if impl else ATTN_IMPL  # 0 = library default; 1 resident keys, 2 flash (P via smem), 3 flash (P in TMEM)
     with _Timed("attn_short", 4.0 * num_seqs * Lq * Lk * num_heads * head_dim):  # QK^T + PV FLOPs
         _check(_lib.osb_attn_short(C.byref(a), _stream()), "osb_attn_short")

@@ -19,11 +19,12 @@ def _ids(B, Lt, T, H, W):
     return torch.zeros(B, Lt, 3), img.reshape(1, T * H * W, 3).repeat(B, 1, 1)
 
 
-def _rand_model(fused):
+def _rand_model(fused, liger=False):
     from opensora.registry import MODELS, build_module
 
     torch.manual_seed(7)
-    m = build_module(dict(type="flux", fused_qkv=fused, **CFG), MODELS, device_map="cpu", torch_dtype=torch.float32)
+    m = build_module(dict(type="flux", fused_qkv=fused, use_liger_rope=liger, **CFG), MODELS, device_map="cpu",
+                     torch_dtype=torch.float32)
     g = torch.Generator().manual_seed(11)
     with torch.no_grad():
         for n, p in m.named_parameters():
@@ -36,14 +37,18 @@ def _rand_model(fused):
     return m.cuda().to(torch.bfloat16)
 
 
-@pytest.mark.parametrize("fused", [True, False])
-def test_mmdit_model_vs_pinned_oracle(fused):
+@pytest.mark.parametrize("fused,liger,thw", [(True, False, (3, 6, 8)), (False, False, (3, 6, 8)), (False, True, (3, 6, 8)),
+                                              (False, True, (5, 12, 16))])
+def test_mmdit_model_vs_pinned_oracle(fused, liger, thw):
+    """(False, True) = the layout the reference ships (configs/diffusion/inference/256px.py:40-41); the last case has a
+    1000-token joint sequence (streaming attention, 8 key blocks)."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from oracle import mmdit_oracle as M
 
-    m = _rand_model(fused)
-    B, Lt, T, H, W = 2, 40, 3, 6, 8   # joint sequence 40 + 144 = 184 tokens (short-key attention kernel)
+    m = _rand_model(fused, liger)
+    B, Lt = 2, 40
+    T, H, W = thw
     g = torch.Generator().manual_seed(3)
     rb = lambda *s: torch.randn(*s, generator=g).to(torch.bfloat16)  # noqa: E731
     txt_ids, img_ids = _ids(B, Lt, T, H, W)
@@ -52,7 +57,7 @@ def test_mmdit_model_vs_pinned_oracle(fused):
     with torch.no_grad():
         out = m(**{k: v.cuda() for k, v in inp.items()})
     W32 = {k: v.float() for k, v in m.state_dict().items()}
-    cfg = dict(CFG, fused_qkv=fused)
+    cfg = dict(CFG, fused_qkv=fused, use_liger_rope=liger)
     finp = {k: (v.float() if v.is_floating_point() else v).cuda() for k, v in inp.items()}
     ref = M.model_forward(W32, cfg, finp["img"], finp["img_ids"], finp["txt"], finp["txt_ids"], finp["timesteps"],
                           finp["y_vec"], cond=finp["cond"], guidance=finp["guidance"])
@@ -60,7 +65,7 @@ def test_mmdit_model_vs_pinned_oracle(fused):
     binp = {k: v.cuda() for k, v in inp.items()}
     noise = M.model_forward(Wb, cfg, binp["img"], binp["img_ids"], binp["txt"], binp["txt_ids"], binp["timesteps"].to(torch.bfloat16),
                             binp["y_vec"], cond=binp["cond"], guidance=binp["guidance"].to(torch.bfloat16))
-    r, _ = report(f"MMDiT model fused_qkv={fused}", out, ref)
+    r, _ = report(f"MMDiT model fused_qkv={fused} liger={liger} L={Lt + T * H * W}", out, ref)
     rn = rel_l2(noise, ref)
     print(f"[parity] reference-in-bf16 noise floor rel_l2={rn:.3e}")
     assert out.shape == ref.shape
