@@ -170,6 +170,14 @@ typedef struct osb_vae_prep_args {
  * F.pad passes of unet_causal_3d_blocks.py:95,136-150,246-250. */
 int osb_vae_prep(const osb_vae_prep_args* args, void* stream);
 
+/* ---- sampler step --------------------------------------------------------------------- */
+/* pred = uncond2 + g_img*(uncond - uncond2) + g_txt*(cond - uncond)  (uncond2 == NULL: uncond + g_txt*(cond - uncond));
+ * out = x + dt*pred.  bf16 [n] in/out (out may alias x), fp32 math, one rounding.  g_img_map: optional bf16 map of
+ * per-element image guidance repeating with period map_period (temporal oscillation).
+ * Replaces opensora/utils/sampling.py:204-222 (CFG combine + Euler update of I2VDenoiser.denoise). */
+int osb_cfg_euler(const void* cond, const void* uncond, const void* uncond2, const void* x, void* out, int64_t n,
+                  float g_txt, float g_img, const void* g_img_map, int64_t map_period, float dt, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

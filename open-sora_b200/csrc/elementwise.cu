@@ -125,3 +125,60 @@ extern "C" int osb_ln_modulate(const void* x, const float* shift, const float* s
   set_error("osb_ln_modulate: unsupported C %d", C);
   return OSB_ERR_UNSUPPORTED;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// osb_cfg_euler: classifier-free-guidance combine + Euler step of the rectified-flow sampler in ONE pass:
+//   pred = uncond2 + g_img * (uncond - uncond2) + g_txt * (cond - uncond)      (uncond2 == NULL: uncond + g_txt * (cond - uncond))
+//   out  = x + dt * pred
+// bf16 in/out, fp32 math, one rounding (the reference rounds after each of the ~7 torch ops).  g_img may be a
+// per-element bf16 map (temporal oscillation, sampling.py:208-217) that repeats with period `map_period`.
+// Replaces opensora/utils/sampling.py:204-222 (I2VDenoiser.denoise update).  HBM bound: 5 tensors x 2 B/element.
+// ------------------------------------------------------------------------------------------------------------
+namespace osb {
+__global__ void __launch_bounds__(256)
+cfg_euler_kernel(const uint4* __restrict__ c, const uint4* __restrict__ u, const uint4* __restrict__ u2,
+                 const uint4* __restrict__ x, uint4* __restrict__ out, int64_t nvec, float g_txt, float g_img,
+                 const uint4* __restrict__ g_map, int64_t map_vecs, float dt) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 cv = c[i], uv = u[i], xv = x[i];
+    const uint4 u2v = u2 ? u2[i] : uv;
+    const uint4 gv = g_map ? g_map[i % map_vecs] : make_uint4(0, 0, 0, 0);
+    const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w}, uw[4] = {uv.x, uv.y, uv.z, uv.w}, vw[4] = {u2v.x, u2v.y, u2v.z, u2v.w};
+    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 cf = unpack_bf16x2(cw[e]), uf = unpack_bf16x2(uw[e]), vf = unpack_bf16x2(vw[e]), xf = unpack_bf16x2(xw[e]);
+      float2 gi = make_float2(g_img, g_img);
+      if (g_map) gi = unpack_bf16x2(gw[e]);
+      const float p0 = vf.x + gi.x * (uf.x - vf.x) + g_txt * (cf.x - uf.x);
+      const float p1 = vf.y + gi.y * (uf.y - vf.y) + g_txt * (cf.y - uf.y);
+      ow[e] = pack_bf16x2(xf.x + dt * p0, xf.y + dt * p1);
+    }
+    out[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+}
+}  // namespace osb
+
+extern "C" int osb_cfg_euler(const void* cond, const void* uncond, const void* uncond2, const void* x, void* out, int64_t n,
+                             float g_txt, float g_img, const void* g_img_map, int64_t map_period, float dt, void* stream) {
+  using namespace osb;
+  if (!initialised()) { set_error("osb_init() has not been called"); return OSB_ERR_NOT_INIT; }
+  OSB_REQUIRE(cond && uncond && x && out, "osb_cfg_euler: null tensor");
+  OSB_REQUIRE(n > 0 && n % 8 == 0, "osb_cfg_euler: element count must be a positive multiple of 8");
+  OSB_REQUIRE(g_img_map == nullptr || (map_period > 0 && map_period % 8 == 0 && n % map_period == 0),
+              "osb_cfg_euler: guidance map period must be a multiple of 8 dividing n");
+  OSB_REQUIRE(((reinterpret_cast<uintptr_t>(cond) | reinterpret_cast<uintptr_t>(uncond) | reinterpret_cast<uintptr_t>(uncond2) |
+                reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(g_img_map)) & 15) == 0,
+              "osb_cfg_euler: tensors must be 16-byte aligned");
+  const int64_t nvec = n / 8;
+  int64_t blocks = (nvec + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+  cfg_euler_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(cond), static_cast<const uint4*>(uncond), static_cast<const uint4*>(uncond2),
+      static_cast<const uint4*>(x), static_cast<uint4*>(out), nvec, g_txt, g_img, static_cast<const uint4*>(g_img_map),
+      g_img_map ? map_period / 8 : 1, dt);
+  OSB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OSB_OK;
+}

@@ -25,6 +25,7 @@ EXPORTS = (
     "osb_group_stats",
     "osb_group_stats_workspace_bytes",
     "osb_vae_prep",
+    "osb_cfg_euler",
 )
 
 EPI_BIAS, EPI_BIAS_GELU_TANH, EPI_BIAS_GATE_RES = 0, 1, 2
@@ -56,6 +57,8 @@ def _load() -> C.CDLL:
     lib.osb_attn_short.argtypes = [C.c_void_p, C.c_void_p]
     lib.osb_conv3d_ndhwc.argtypes = [C.c_void_p, C.c_void_p]
     lib.osb_vae_prep.argtypes = [C.c_void_p, C.c_void_p]
+    lib.osb_cfg_euler.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
+                                  C.c_float, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]
     lib.osb_group_stats.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
                                     C.c_int64, C.c_void_p, C.c_void_p]
     lib.osb_group_stats_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int32]
@@ -393,3 +396,20 @@ def pack_conv_weight(w, cp: int, narrow: bool, cout_pad: int | None = None):
     out = torch.zeros(co, kt, kh, kw, cp, dtype=w.dtype, device=w.device)
     out[:cout, ..., :cin] = w.permute(0, 2, 3, 4, 1)
     return out.reshape(co, kt * kh * kw * cp).to(torch.bfloat16).contiguous()
+
+
+def cfg_euler(cond, uncond, uncond2, x, *, g_txt: float, g_img: float = 1.0, g_img_map=None, dt: float, out=None):
+    """out = x + dt * (uncond2 + g_img*(uncond - uncond2) + g_txt*(cond - uncond)); bf16 tensors of one shape."""
+    import torch
+
+    for t, n in ((cond, "cond"), (uncond, "uncond"), (uncond2, "uncond2"), (x, "x"), (g_img_map, "g_img_map")):
+        _need(t, torch.bfloat16, n)
+        assert t is None or t.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    n = x.numel()
+    with _Timed("cfg_euler", 2.0 * n * (5 if uncond2 is not None else 4)):
+        _check(_lib.osb_cfg_euler(_ptr(cond), _ptr(uncond), _ptr(uncond2), _ptr(x), _ptr(out), n, g_txt, g_img,
+                                  _ptr(g_img_map), g_img_map.numel() if g_img_map is not None else 0, dt, _stream()),
+               "osb_cfg_euler")
+    return out
