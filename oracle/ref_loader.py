@@ -178,3 +178,39 @@ def load_hunyuan_vae():
                   or k.startswith("diffusers.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def load_sampling():
+    """The reference's `opensora/utils/sampling.py` executed by path.  Its top-level imports that are absent here
+    (mmengine, peft, datasets, text encoder, registry, inference helpers) are only used by the prompt / model-loading
+    half of the file; they are replaced by empty stand-ins.  The numeric functions used for goldens
+    (`time_shift`, `get_schedule`, `pack`, `unpack`, `get_oscillation_gs`, `I2VDenoiser.denoise`) are untouched."""
+    import enum
+
+    names = ("opensora", "opensora.utils", "opensora.datasets", "opensora.models", "opensora.models.mmdit",
+             "opensora.models.text", "mmengine", "peft")
+    saved = {k: v for k, v in sys.modules.items() if any(k == n or k.startswith(n + ".") for n in ("opensora", "mmengine", "peft"))}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        for n in names:
+            _shell(n)
+
+        def mod(name, **attrs):
+            m = types.ModuleType(name)
+            m.__dict__.update(attrs)
+            sys.modules[name] = m
+
+        mod("mmengine.config", Config=type("Config", (), {}))
+        sys.modules["peft"].PeftModel = type("PeftModel", (), {})
+        mod("opensora.datasets.aspect", get_image_size=lambda *a, **k: (0, 0))
+        mod("opensora.models.mmdit.model", MMDiTModel=type("MMDiTModel", (), {}))
+        mod("opensora.models.text.conditioner", HFEmbedder=type("HFEmbedder", (), {}))
+        mod("opensora.registry", MODELS=None, build_module=None)
+        mod("opensora.utils.inference", SamplingMethod=enum.Enum("SamplingMethod", {"I2V": "i2v", "DISTILLED": "distill"}),
+            collect_references_batch=None, prepare_inference_condition=None)
+        return _load("opensora.utils.sampling", os.path.join(REF, "opensora", "utils", "sampling.py"))
+    finally:
+        for k in [k for k in sys.modules if any(k == n or k.startswith(n + ".") for n in ("opensora", "mmengine", "peft"))]:
+            del sys.modules[k]
+        sys.modules.update(saved)
