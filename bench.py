@@ -151,17 +151,19 @@ def run_reference(args, rank):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def build_model(device):
+    """Random-init STDiT3-XL/2 built and initialised ON the device (1.1 B parameters: CPU init would take minutes
+    per rank; there are no checkpoints offline)."""
     from opensora.registry import MODELS, build_module
 
-    torch.manual_seed(1234)
-    m = build_module(dict(type="STDiT3-XL/2"), MODELS).eval()
-    g = torch.Generator().manual_seed(1234)
-    with torch.no_grad():  # random-init weights of the named architecture (no checkpoints offline)
+    with torch.device(device):
+        m = build_module(dict(type="STDiT3-XL/2"), MODELS).eval()
+    g = torch.Generator(device=device).manual_seed(1234)
+    with torch.no_grad():
         for n, p in m.named_parameters():
             if p.dim() >= 2 and "scale_shift_table" not in n:
-                p.copy_(torch.randn(p.shape, generator=g) * (0.7 / (p[0].numel() ** 0.5)))
+                p.copy_(torch.randn(p.shape, generator=g, device=device) * (0.7 / (p[0].numel() ** 0.5)))
             elif n.endswith("bias"):
-                p.copy_(0.02 * torch.randn(p.shape, generator=g))
+                p.copy_(0.02 * torch.randn(p.shape, generator=g, device=device))
     return m.to(device=device, dtype=torch.bfloat16)
 
 
@@ -189,7 +191,8 @@ def vae_leg():
         from opensora.registry import MODELS, build_module
 
         torch.manual_seed(0)
-        m = build_module(dict(type="hunyuan_vae"), MODELS, device_map="cuda").eval()
+        with torch.device("cuda"):
+            m = build_module(dict(type="hunyuan_vae"), MODELS, device_map="cuda").eval()
         with torch.no_grad():
             z = torch.randn(1, 16, 17, 90, 160, device="cuda").to(torch.bfloat16)
             m.decode(z)

@@ -96,18 +96,30 @@ __device__ __forceinline__ uint4 pack8(const float* x) {
   return o;
 }
 
+__device__ __forceinline__ float sumsq8(const uint4& t) {
+  float x[8];
+  unpack8(t, x);
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s += x[e] * x[e];
+  return s;
+}
+
 // Units [UB, UE) of one head row, given as raw bf16x8 registers: optional RMSNorm scale r*w and RoPE in
 // fp32 -> bf16 -> K-major operand tile (main chunks swizzled, tail no-swizzle); units >= U are zero pad.
 template <int D, int UB, int UE>
-__device__ __forceinline__ void finish_and_store_units(const uint4* raw, float r, const __nv_bfloat16* w,
-                                                       const float* cosr, const float* sinr, uint8_t* main_base,
-                                                       int main_chunk_bytes, uint8_t* tail_base, int row) {
+__device__ __forceinline__ float finish_and_store_units(const uint4* raw, float r, const __nv_bfloat16* w,
+                                                        const float* cosr, const float* sinr, uint8_t* main_base,
+                                                        int main_chunk_bytes, uint8_t* tail_base, int row,
+                                                        bool want_norm = false) {
   using Cfg = AttnCfg<D>;
+  float nrm2 = 0.f;  // squared length of the staged vector part (RoPE is a rotation: measured before it)
 #pragma unroll
   for (int u = UB; u < UE; ++u) {
     uint4 o;
     if (u < Cfg::U) {
       o = raw[u - UB];
+      if (w == nullptr && cosr == nullptr && want_norm) nrm2 += sumsq8(o);
       if (w != nullptr || cosr != nullptr) {
         float xu[8];
         unpack8(o, xu);
@@ -116,6 +128,10 @@ __device__ __forceinline__ void finish_and_store_units(const uint4* raw, float r
           unpack8(__ldg(reinterpret_cast<const uint4*>(w) + u), wf);
 #pragma unroll
           for (int e = 0; e < 8; ++e) xu[e] *= r * wf[e];
+        }
+        if (want_norm) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) nrm2 += xu[e] * xu[e];
         }
         if (cosr != nullptr) {
           const float4 c4 = __ldg(reinterpret_cast<const float4*>(cosr) + u);
@@ -138,6 +154,7 @@ __device__ __forceinline__ void finish_and_store_units(const uint4* raw, float r
     else
       *reinterpret_cast<uint4*>(tail_base + tail_off(row, u - Cfg::MAIN * 8)) = o;
   }
+  return nrm2;
 }
 
 // Full head row with rotate-half RoPE (LigerRopeFunction, math.py:27): element i pairs with i + D/2, so units u and
@@ -182,15 +199,6 @@ __device__ __forceinline__ void finish_and_store_row_half(const uint4* raw, floa
     *reinterpret_cast<uint4*>(tail_base + tail_off(row, u - Cfg::MAIN * 8)) = make_uint4(0, 0, 0, 0);
 }
 
-__device__ __forceinline__ float sumsq8(const uint4& t) {
-  float x[8];
-  unpack8(t, x);
-  float s = 0.f;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) s += x[e] * x[e];
-  return s;
-}
-
 template <int D>
 __global__ void __launch_bounds__(kAttnThreads, (D <= 72) ? 2 : 1) attn_short_kernel(const AttnParams p) {
   using Cfg = AttnCfg<D>;
@@ -206,7 +214,9 @@ __global__ void __launch_bounds__(kAttnThreads, (D <= 72) ? 2 : 1) attn_short_ke
   uint8_t* sP = smem + p.off_p;        // ceil(NKP/64) chunks of [128 x 64]
   float* xch = reinterpret_cast<float*>(smem + p.off_misc);          // [2][128] pair exchange (ss / max)
   float* xsum = xch + 256;                                           // [2][128] partial row sums
-  const uint32_t bar_s = smem_u32(smem + p.off_misc + 2048);
+  float* xqn = xch + 512;                                            // [2][128] partial |q|^2 of the staged rows
+  uint32_t* kmax2 = reinterpret_cast<uint32_t*>(xch + 768);          // max |k|^2 over the staged keys (float bits)
+  const uint32_t bar_s = smem_u32(smem + p.off_misc + 3200);
   const uint32_t bar_o = bar_s + 8;
   const uint32_t tmem_slot = bar_s + 16;
   const int k_chunk_bytes = p.NKP * 128;
@@ -224,10 +234,12 @@ __global__ void __launch_bounds__(kAttnThreads, (D <= 72) ? 2 : 1) attn_short_ke
       mbar_init(bar_s, 1);
       mbar_init(bar_o, 1);
       fence_barrier_init();
+      *kmax2 = 0u;
     }
     __syncwarp();
     tmem_alloc<1>(tmem_slot, (uint32_t)p.tmem_cols);
   }
+  __syncthreads();  // kmax2 is zeroed before any key's atomicMax
 
   // ---- which sequences / q-tiles does this CTA cover --------------------------------------
   int64_t seq0;
@@ -269,8 +281,10 @@ __global__ void __launch_bounds__(kAttnThreads, (D <= 72) ? 2 : 1) attn_short_ke
       rk = rsqrtf(ss * (1.0f / D) + p.eps);
     }
     const __nv_bfloat16* kwt = (p.kw2 != nullptr && ktok >= p.norm_split) ? p.kw2 : p.kw;
-    finish_and_store_units<D, 0, UP>(tk, rk, kwt, p.cos ? p.cos + (int64_t)ktok * (D / 2) : nullptr,
-                                     p.sin ? p.sin + (int64_t)ktok * (D / 2) : nullptr, sK, k_chunk_bytes, sKt, slot);
+    const float kn2 = finish_and_store_units<D, 0, UP>(tk, rk, kwt, p.cos ? p.cos + (int64_t)ktok * (D / 2) : nullptr,
+                                                       p.sin ? p.sin + (int64_t)ktok * (D / 2) : nullptr, sK, k_chunk_bytes,
+                                                       sKt, slot, true);
+    atomicMax(kmax2, __float_as_uint(kn2));  // non-negative floats order like their bit patterns
     // V^T: raw bf16 halves go straight to their transposed position (no fp32 round trip)
     uint8_t* vt = sVt + (slot >> 6) * vt_chunk_bytes + (slot & 7) * 2;
     const int ku = (slot & 63) >> 3;
@@ -334,8 +348,10 @@ __global__ void __launch_bounds__(kAttnThreads, (D <= 72) ? 2 : 1) attn_short_ke
       const float* cq = p.cos ? p.cos + (int64_t)qtok * (D / 2) : nullptr;
       const float* sq = p.sin ? p.sin + (int64_t)qtok * (D / 2) : nullptr;
       const __nv_bfloat16* qwt = (p.qw2 != nullptr && qtok >= p.norm_split) ? p.qw2 : p.qw;
-      if (part == 0) finish_and_store_units<D, 0, U0>(t, rq, qwt, cq, sq, sQ, 128 * 128, sQt, r);
-      else finish_and_store_units<D, U0, UP>(t, rq, qwt, cq, sq, sQ, 128 * 128, sQt, r);
+      float qn2;
+      if (part == 0) qn2 = finish_and_store_units<D, 0, U0>(t, rq, qwt, cq, sq, sQ, 128 * 128, sQt, r, true);
+      else qn2 = finish_and_store_units<D, U0, UP>(t, rq, qwt, cq, sq, sQ, 128 * 128, sQt, r, true);
+      xqn[part * 128 + r] = qn2;
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -379,26 +395,33 @@ __global__ void __launch_bounds__(kAttnThreads, (D <= 72) ? 2 : 1) attn_short_ke
     // tcgen05.ld is warp-collective: skip decisions use the union of the warp's key ranges
     const int w_lo = __reduce_min_sync(0xffffffffu, q_valid ? key_lo : 0x7fffffff);
     const int w_hi = __reduce_max_sync(0xffffffffu, q_valid ? key_hi : 0);
+    // Softmax is shift invariant: any shift >= the row maximum that does not underflow everything is exact.
+    // Cauchy-Schwarz gives one for free, |q| max|k| >= max_j q.k_j; when it is within 2^64 of fp32 range (it is for
+    // RMS-normed q,k) the separate row-maximum pass over S (one TMEM read + compare per element) is skipped.
+    const float bound = sqrtf((xqn[r] + xqn[128 + r]) * __uint_as_float(*kmax2)) * fabsf(p.scale_log2);
+    const bool one_pass = __all_sync(0xffffffffu, bound < 64.f);
     float mx = -INFINITY;
-    for (int c = c_begin; c < c_end; ++c) {
-      const int c0 = c * 32;
-      if (c0 >= w_hi || c0 + 32 <= w_lo) continue;
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(t_row + c0, v);
-      tmem_ld_wait();
-      if (c0 >= key_lo && c0 + 32 <= key_hi) {
+    if (!one_pass) {
+      for (int c = c_begin; c < c_end; ++c) {
+        const int c0 = c * 32;
+        if (c0 >= w_hi || c0 + 32 <= w_lo) continue;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + c0, v);
+        tmem_ld_wait();
+        if (c0 >= key_lo && c0 + 32 <= key_hi) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-      } else {
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j >= key_lo && c0 + j < key_hi) mx = fmaxf(mx, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j >= key_lo && c0 + j < key_hi) mx = fmaxf(mx, __uint_as_float(v[j]));
+        }
       }
     }
     xch[part * 128 + r] = mx;
-    __syncthreads();
+    __syncthreads();   // (also orders the pair's reads of xqn/kmax2 before the next q-tile's writes)
     mx = fmaxf(xch[r], xch[128 + r]);
-    const float mscaled = (mx == -INFINITY) ? 0.f : mx * p.scale_log2;
+    const float mscaled = one_pass ? bound : ((mx == -INFINITY) ? 0.f : mx * p.scale_log2);
     float sum = 0.f;
     for (int c = c_begin; c < c_end; ++c) {
       const int c0 = c * 32;
@@ -413,13 +436,13 @@ __global__ void __launch_bounds__(kAttnThreads, (D <= 72) ? 2 : 1) attn_short_ke
         if (c0 >= key_lo && c0 + 32 <= key_hi) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            pr[j] = exp2f(__uint_as_float(v[j]) * p.scale_log2 - mscaled);
+            pr[j] = fast_exp2(__uint_as_float(v[j]) * p.scale_log2 - mscaled);
             sum += pr[j];
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float e = exp2f(__uint_as_float(v[j]) * p.scale_log2 - mscaled);
+            const float e = fast_exp2(__uint_as_float(v[j]) * p.scale_log2 - mscaled);
             pr[j] = (c0 + j >= key_lo && c0 + j < key_hi) ? e : 0.f;
             sum += pr[j];
           }
@@ -626,7 +649,7 @@ __global__ void __launch_bounds__(kFlashThreads, (D <= 72) ? 2 : 1) attn_flash_k
           if (jb > 0) {
             mbar_wait(o_full, n_o & 1); ++n_o;
             tc_fence_after();
-            const float alpha = (m == -INFINITY) ? 1.f : exp2f(m * p.scale_log2 - ms);
+            const float alpha = (m == -INFINITY) ? 1.f : fast_exp2(m * p.scale_log2 - ms);
             if (__any_sync(0xffffffffu, alpha != 1.f)) {
 #pragma unroll 1
               for (int c = 0; c < Cfg::DP; c += 8) {
@@ -652,17 +675,17 @@ __global__ void __launch_bounds__(kFlashThreads, (D <= 72) ? 2 : 1) attn_flash_k
               float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;  // four chains: the adds do not serialise
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                pr[j] = exp2f(__uint_as_float(v[j]) * p.scale_log2 - ms); l0 += pr[j];
-                pr[j + 1] = exp2f(__uint_as_float(v[j + 1]) * p.scale_log2 - ms); l1 += pr[j + 1];
-                pr[j + 2] = exp2f(__uint_as_float(v[j + 2]) * p.scale_log2 - ms); l2 += pr[j + 2];
-                pr[j + 3] = exp2f(__uint_as_float(v[j + 3]) * p.scale_log2 - ms); l3 += pr[j + 3];
+                pr[j] = fast_exp2(__uint_as_float(v[j]) * p.scale_log2 - ms); l0 += pr[j];
+                pr[j + 1] = fast_exp2(__uint_as_float(v[j + 1]) * p.scale_log2 - ms); l1 += pr[j + 1];
+                pr[j + 2] = fast_exp2(__uint_as_float(v[j + 2]) * p.scale_log2 - ms); l2 += pr[j + 2];
+                pr[j + 3] = fast_exp2(__uint_as_float(v[j + 3]) * p.scale_log2 - ms); l3 += pr[j + 3];
               }
               l += (l0 + l1) + (l2 + l3);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const bool ok = ka + j >= key_lo && ka + j < key_hi && c0 + j < g.BK;
-                pr[j] = ok ? exp2f(__uint_as_float(v[j]) * p.scale_log2 - ms) : 0.f;
+                pr[j] = ok ? fast_exp2(__uint_as_float(v[j]) * p.scale_log2 - ms) : 0.f;
                 l += pr[j];
               }
             }
@@ -925,7 +948,7 @@ static int attn_launch(AttnParams& p, int64_t units, int H, cudaStream_t stream)
   p.off_kt = off; off += up1k(Cfg::TAIL ? p.NKP * 32 : 0);
   p.off_vt = off; off += up1k(nkc * Cfg::DP * 128);
   p.off_p = off; off += nkc * 128 * 128;
-  p.off_misc = off; off += 2048 + 64;
+  p.off_misc = off; off += 3200 + 64;
   const int smem = off;
   const int s_cols = (p.NKP + 31) / 32 * 32;
   p.o_col = s_cols;

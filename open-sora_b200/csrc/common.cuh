@@ -352,6 +352,14 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+// 2^x as ONE MUFU op (exp2f() adds a denormal-range fix-up: 3 extra instructions per element in softmax loops);
+// results below 2^-126 flush to zero, which is what a softmax weight that small should be.
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // GELU, tanh approximation (torch.nn.GELU(approximate="tanh"); layers.py:279).  tanh.approx.f32 is one
 // MUFU op with ~2^-11 relative error - an order of magnitude below the bf16 rounding of the result.
 __device__ __forceinline__ float gelu_tanh(float x) {

@@ -26,7 +26,8 @@ def run(T=65, H=720, W=1280, iters=2, do_encode=True):
     from opensora.registry import MODELS, build_module
 
     torch.manual_seed(0)
-    vae = build_module(dict(type="hunyuan_vae"), MODELS, device_map="cuda").eval()
+    with torch.device("cuda"):  # initialise the 246 M parameters on the device, not on the host
+        vae = build_module(dict(type="hunyuan_vae"), MODELS, device_map="cuda").eval()
     g = torch.Generator(device="cuda").manual_seed(1)
     lt, lh, lw = vae.get_latent_size([T, H, W])
     z = torch.randn(1, 16, lt, lh, lw, device="cuda", generator=g).to(torch.bfloat16)
