@@ -3,10 +3,11 @@
 `"hunyuan_vae"`, `encode / decode / forward / get_latent_size`, `scale_factor`, `shift_factor`, `z_channels`,
 compression ratios, tiling toggles, identical state-dict keys — arithmetic on libosb200 (sm_100a).
 
-Round-1 scope: the UNTILED path (`:298-304`, `:318-335`).  B200's 180 GB holds a 65x720x1280 decode untiled, which is
-also the faster path (no ~1.65x tile-overlap recompute); the tiled/blended mode (`:384-552`), whose numerics differ from
-untiled by construction (per-tile GroupNorm statistics), is SURVEY.md §8(f)-3 and raises NotImplementedError when a
-caller enables it AND the input exceeds the tile thresholds."""
+Untiled (`:298-304`, `:318-335`) is the fast path on B200 (a 65x720x1280 decode peaks at 87 GB of the 180 GB and
+avoids the ~1.65x tile-overlap recompute).  The reference's tiled / blended modes (`:384-552`) are reproduced with the
+same tile grid, overlap, in-place blending order and cropping, because their numerics differ from untiled by
+construction (per-tile GroupNorm statistics and causal start) and a caller that enables tiling must get the
+reference's result; every tile runs through the same osb200 encoder / decoder."""
 from __future__ import annotations
 
 from dataclasses import dataclass
@@ -106,13 +107,6 @@ class AutoencoderKLCausal3D(nn.Module):
             raise osb200.OsbError("AutoencoderKLCausal3D (osb200) runs on CUDA in bfloat16 only; no CPU / eager fallback")
         return osb200
 
-    def _tiled(self, t, h, w, latent: bool):
-        mt = self.tile_latent_min_tsize if latent else self.tile_sample_min_tsize
-        ms = self.tile_latent_min_size if latent else self.tile_sample_min_size
-        if (self.use_temporal_tiling and t > mt) or (self.use_spatial_tiling and (h > ms or w > ms)):
-            raise NotImplementedError("tiled VAE encode/decode (autoencoder_kl_causal_3d.py:384-552) is SURVEY.md §8(f)-3; "
-                                      "call disable_tiling(): the untiled path fits in B200 HBM")
-
     @staticmethod
     def _to_ndhwc(x, cpad=None):
         x = x.permute(0, 2, 3, 4, 1)
@@ -124,32 +118,137 @@ class AutoencoderKLCausal3D(nn.Module):
     def _to_ncdhw(x):
         return x.permute(0, 4, 1, 2, 3).contiguous()
 
+    # ---- tile-level building blocks (NCDHW in / out, bf16) ----------------------------------------------------
+    def _encode_moments(self, x):
+        """encoder + quant_conv on one (tile of a) video -> moments [B, 2*latent, T', h, w]."""
+        osb = self._check()
+        h = self.encoder(self._to_ndhwc(x, cpad=8))
+        nb, T, H, W, C2 = h.shape
+        m = osb.gemm(h.reshape(-1, C2), self.quant_conv.weight.reshape(C2, C2), self.quant_conv.bias)
+        return self._to_ncdhw(m.view(nb, T, H, W, C2))
+
+    def _decode_tile(self, z):
+        """post_quant_conv + decoder on one (tile of a) latent."""
+        osb = self._check()
+        zl = self._to_ndhwc(z)
+        nb, T, H, W, C = zl.shape
+        zl = osb.gemm(zl.reshape(-1, C), self.post_quant_conv.weight.reshape(C, C), self.post_quant_conv.bias)
+        return self._to_ncdhw(self.decoder(zl.view(nb, T, H, W, C)))
+
+    @staticmethod
+    def _blend(a, b, extent, dim):
+        """blend_v / blend_h / blend_t (:360-382): linear cross-fade of the first `extent` slices of `b` (in place) with
+        the last `extent` slices of `a` along `dim`; one vectorised lerp instead of a Python loop per slice."""
+        extent = min(a.shape[dim], b.shape[dim], extent)
+        if extent <= 0:
+            return b
+        w = (torch.arange(extent, device=b.device, dtype=torch.float32) / extent).view([-1 if d == dim % 5 else 1 for d in range(5)])
+        bs = b.narrow(dim, 0, extent)
+        bs.copy_(a.narrow(dim, a.shape[dim] - extent, extent).float() * (1 - w) + bs.float() * w)
+        return b
+
+    def spatial_tiled_encode(self, x, return_moments: bool = False):
+        """:384-434."""
+        overlap = int(self.tile_sample_min_size * (1 - self.tile_overlap_factor))
+        blend = int(self.tile_latent_min_size * self.tile_overlap_factor)
+        limit = self.tile_latent_min_size - blend
+        ts = self.tile_sample_min_size
+        rows = [[self._encode_moments(x[:, :, :, i:i + ts, j:j + ts]) for j in range(0, x.shape[-1], overlap)]
+                for i in range(0, x.shape[-2], overlap)]
+        moments = self._stitch(rows, blend, limit)
+        return moments if return_moments else DiagonalGaussianDistribution(moments)
+
+    def spatial_tiled_decode(self, z):
+        """:436-484."""
+        overlap = int(self.tile_latent_min_size * (1 - self.tile_overlap_factor))
+        blend = int(self.tile_sample_min_size * self.tile_overlap_factor)
+        limit = self.tile_sample_min_size - blend
+        tl = self.tile_latent_min_size
+        rows = [[self._decode_tile(z[:, :, :, i:i + tl, j:j + tl]) for j in range(0, z.shape[-1], overlap)]
+                for i in range(0, z.shape[-2], overlap)]
+        return self._stitch(rows, blend, limit)
+
+    def _stitch(self, rows, blend, limit):
+        out_rows = []
+        for i, row in enumerate(rows):
+            out = []
+            for j, tile in enumerate(row):
+                if i > 0:
+                    tile = self._blend(rows[i - 1][j], tile, blend, -2)
+                if j > 0:
+                    tile = self._blend(row[j - 1], tile, blend, -1)
+                out.append(tile[:, :, :, :limit, :limit])
+            out_rows.append(torch.cat(out, dim=-1))
+        return torch.cat(out_rows, dim=-2)
+
+    def temporal_tiled_encode(self, x):
+        """:486-515."""
+        overlap = int(self.tile_sample_min_tsize * (1 - self.tile_overlap_factor))
+        blend = int(self.tile_latent_min_tsize * self.tile_overlap_factor)
+        t_limit = self.tile_latent_min_tsize - blend
+        row = []
+        for i in range(0, x.shape[2], overlap):
+            tile = x[:, :, i:i + self.tile_sample_min_tsize + 1]
+            if self.use_spatial_tiling and (tile.shape[-1] > self.tile_sample_min_size or tile.shape[-2] > self.tile_sample_min_size):
+                tile = self.spatial_tiled_encode(tile, return_moments=True)
+            else:
+                tile = self._encode_moments(tile)
+            row.append(tile[:, :, 1:] if i > 0 else tile)
+        return DiagonalGaussianDistribution(self._stitch_t(row, blend, t_limit))
+
+    def temporal_tiled_decode(self, z):
+        """:517-548."""
+        overlap = int(self.tile_latent_min_tsize * (1 - self.tile_overlap_factor))
+        blend = int(self.tile_sample_min_tsize * self.tile_overlap_factor)
+        t_limit = self.tile_sample_min_tsize - blend
+        row = []
+        for i in range(0, z.shape[2], overlap):
+            tile = z[:, :, i:i + self.tile_latent_min_tsize + 1]
+            if self.use_spatial_tiling and (tile.shape[-1] > self.tile_latent_min_size or tile.shape[-2] > self.tile_latent_min_size):
+                dec = self.spatial_tiled_decode(tile)
+            else:
+                dec = self._decode_tile(tile)
+            row.append(dec[:, :, 1:] if i > 0 else dec)
+        return self._stitch_t(row, blend, t_limit)
+
+    def _stitch_t(self, row, blend, t_limit):
+        out = []
+        for i, tile in enumerate(row):
+            if i > 0:
+                tile = self._blend(row[i - 1], tile, blend, 2)
+                out.append(tile[:, :, :t_limit])
+            else:
+                out.append(tile[:, :, :t_limit + 1])
+        return torch.cat(out, dim=2)
+
     # ---- public API (:269-358, :554-622) -------------------------------------------------------------------
     def encode(self, x, sample_posterior=True, return_posterior=False, generator=None):
-        osb = self._check()
+        self._check()
         assert x.dim() == 5, "The input tensor should have 5 dimensions."
-        self._tiled(x.shape[2], x.shape[3], x.shape[4], latent=False)
-        dev = self.quant_conv.weight.device
-        xin = self._to_ndhwc(x.to(dev, torch.bfloat16), cpad=8)
-        h = self.encoder(xin)                                                  # [B,T',h,w,2*latent]
-        nb, T, H, W, C2 = h.shape
-        qw = self.quant_conv.weight.reshape(C2, C2)
-        moments = osb.gemm(h.reshape(-1, C2), qw, self.quant_conv.bias).view(nb, T, H, W, C2)
-        posterior = DiagonalGaussianDistribution(self._to_ncdhw(moments))
+        x = x.to(self.quant_conv.weight.device, torch.bfloat16)
+        if self.use_temporal_tiling and x.shape[2] > self.tile_sample_min_tsize:
+            posterior = self.temporal_tiled_encode(x)
+        elif self.use_spatial_tiling and (x.shape[-1] > self.tile_sample_min_size or x.shape[-2] > self.tile_sample_min_size):
+            posterior = self.spatial_tiled_encode(x)
+        else:
+            posterior = DiagonalGaussianDistribution(self._encode_moments(x))
         z = posterior.sample(generator=generator) if sample_posterior else posterior.mode()
         z = self.scale_factor * (z - self.shift_factor)
         return (z, posterior) if return_posterior else z
 
+    def _decode(self, z):
+        if self.use_temporal_tiling and z.shape[2] > self.tile_latent_min_tsize:
+            return self.temporal_tiled_decode(z)
+        if self.use_spatial_tiling and (z.shape[-1] > self.tile_latent_min_size or z.shape[-2] > self.tile_latent_min_size):
+            return self.spatial_tiled_decode(z)
+        return self._decode_tile(z)
+
     def decode(self, z):
-        osb = self._check()
-        self._tiled(z.shape[2], z.shape[3], z.shape[4], latent=True)
-        dev = self.quant_conv.weight.device
-        z = z.to(dev, torch.bfloat16) / self.scale_factor + self.shift_factor
-        zl = self._to_ndhwc(z)
-        nb, T, H, W, C = zl.shape
-        pw = self.post_quant_conv.weight.reshape(C, C)
-        zl = osb.gemm(zl.reshape(-1, C), pw, self.post_quant_conv.bias).view(nb, T, H, W, C)
-        return self._to_ncdhw(self.decoder(zl))
+        self._check()
+        z = z.to(self.quant_conv.weight.device, torch.bfloat16) / self.scale_factor + self.shift_factor
+        if self.use_slicing and z.shape[0] > 1:
+            return torch.cat([self._decode(zs) for zs in z.split(1)])
+        return self._decode(z)
 
     def forward(self, x, sample_posterior=True, generator=None):
         z, posterior = self.encode(x, return_posterior=True, sample_posterior=sample_posterior, generator=generator)

@@ -85,7 +85,7 @@ def load_mmdit():
         sys.modules.update(saved)
 
 
-def load_hunyuan_vae():
+def load_hunyuan_vae(with_autoencoder: bool = False):
     """Returns (blocks, vae) = the reference's `hunyuan_vae/unet_causal_3d_blocks.py` and `hunyuan_vae/vae.py`
     executed by path, with stand-ins for the third-party `diffusers` pieces they import (absent in this image;
     the reference pins nothing - header says "Modified from diffusers==0.29.2", unet_causal_3d_blocks.py:1):
@@ -172,7 +172,40 @@ def load_hunyuan_vae():
         blocks = _load("opensora.models.hunyuan_vae.unet_causal_3d_blocks",
                        os.path.join(base, "hunyuan_vae", "unet_causal_3d_blocks.py"))
         vae = _load("opensora.models.hunyuan_vae.vae", os.path.join(base, "hunyuan_vae", "vae.py"))
-        return blocks, vae
+        if not with_autoencoder:
+            return blocks, vae
+        # autoencoder_kl_causal_3d.py additionally needs the diffusers Mixin plumbing (config registration, hub
+        # loading, forward hooks): none of it touches arithmetic, so empty stand-ins suffice.
+        _shell("diffusers.loaders")
+        _shell("opensora.utils")
+        cu = types.ModuleType("diffusers.configuration_utils")
+        cu.ConfigMixin = type("ConfigMixin", (), {})
+        cu.register_to_config = lambda f: f
+        sys.modules["diffusers.configuration_utils"] = cu
+        sys.modules["diffusers.loaders"].FromOriginalVAEMixin = type("FromOriginalVAEMixin", (), {})
+        for n in ("ADDED_KV_ATTENTION_PROCESSORS", "CROSS_ATTENTION_PROCESSORS", "AttentionProcessor", "AttnAddedKVProcessor",
+                  "AttnProcessor"):
+            setattr(ap, n, type(n, (), {}))
+        mu = types.ModuleType("diffusers.models.modeling_utils")
+        mu.ModelMixin = type("ModelMixin", (nn.Module,), {})
+        sys.modules["diffusers.models.modeling_utils"] = mu
+        au = types.ModuleType("diffusers.utils.accelerate_utils")
+        au.apply_forward_hook = lambda f: f
+        sys.modules["diffusers.utils.accelerate_utils"] = au
+        reg = types.ModuleType("opensora.registry")
+
+        class _R:
+            def register_module(self, *a, **k):
+                return lambda f: f
+
+        reg.MODELS = _R()
+        sys.modules["opensora.registry"] = reg
+        uc = types.ModuleType("opensora.utils.ckpt")
+        uc.load_checkpoint = lambda model, *a, **k: model
+        sys.modules["opensora.utils.ckpt"] = uc
+        ae = _load("opensora.models.hunyuan_vae.autoencoder_kl_causal_3d",
+                   os.path.join(base, "hunyuan_vae", "autoencoder_kl_causal_3d.py"))
+        return blocks, vae, ae
     finally:
         for k in [k for k in sys.modules if k == "opensora" or k.startswith("opensora.") or k == "diffusers"
                   or k.startswith("diffusers.")]:

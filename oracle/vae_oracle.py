@@ -126,3 +126,86 @@ def stage_plan(n_blocks=4, time_compression_ratio=4, spatial_compression_ratio=8
         tu = (i >= n_blocks - 1 - nt) and not final
         up.append((2 if tu else 1, 2 if sp else 1, 2 if sp else 1) if (sp or tu) else None)
     return down, up
+
+
+# ---- tiled / blended modes of AutoencoderKLCausal3D (autoencoder_kl_causal_3d.py:360-552) -------------------------
+def _blend(a, b, extent, dim):
+    """:360-382 blend_v / blend_h / blend_t (in place on b, slice by slice in the reference)."""
+    extent = min(a.shape[dim], b.shape[dim], extent)
+    for k in range(extent):
+        sb, sa = b.select(dim, k), a.select(dim, a.shape[dim] - extent + k)
+        sb.copy_(sa * (1 - k / extent) + sb * (k / extent))
+    return b
+
+
+def _stitch(rows, blend, limit):
+    out_rows = []
+    for i, row in enumerate(rows):
+        out = []
+        for j, tile in enumerate(row):
+            if i > 0:
+                tile = _blend(rows[i - 1][j], tile, blend, -2)
+            if j > 0:
+                tile = _blend(row[j - 1], tile, blend, -1)
+            out.append(tile[:, :, :, :limit, :limit])
+        out_rows.append(torch.cat(out, dim=-1))
+    return torch.cat(out_rows, dim=-2)
+
+
+def _stitch_t(row, blend, t_limit):
+    out = []
+    for i, tile in enumerate(row):
+        if i > 0:
+            tile = _blend(row[i - 1], tile, blend, 2)
+            out.append(tile[:, :, :t_limit])
+        else:
+            out.append(tile[:, :, : t_limit + 1])
+    return torch.cat(out, dim=2)
+
+
+def tiled_autoencoder(enc_fn, dec_fn, sample_size, sample_tsize, n_blocks=4, time_ratio=4, overlap=0.25, spatial=True, temporal=True):
+    """Returns (encode_moments(x), decode(z)) reproducing :269-335 dispatch + :384-552 tiling around per-tile callables
+    enc_fn(x_tile) -> moments and dec_fn(z_tile) -> sample."""
+    ls = int(sample_size / (2 ** (n_blocks - 1)))
+    lt = sample_tsize // time_ratio
+
+    def sp_enc(x):
+        ov, bl = int(sample_size * (1 - overlap)), int(ls * overlap)
+        rows = [[enc_fn(x[:, :, :, i:i + sample_size, j:j + sample_size]) for j in range(0, x.shape[-1], ov)]
+                for i in range(0, x.shape[-2], ov)]
+        return _stitch(rows, bl, ls - bl)
+
+    def sp_dec(z):
+        ov, bl = int(ls * (1 - overlap)), int(sample_size * overlap)
+        rows = [[dec_fn(z[:, :, :, i:i + ls, j:j + ls]) for j in range(0, z.shape[-1], ov)] for i in range(0, z.shape[-2], ov)]
+        return _stitch(rows, bl, sample_size - bl)
+
+    def encode(x):
+        if temporal and x.shape[2] > sample_tsize:
+            ov, bl = int(sample_tsize * (1 - overlap)), int(lt * overlap)
+            row = []
+            for i in range(0, x.shape[2], ov):
+                tile = x[:, :, i:i + sample_tsize + 1]
+                big = spatial and (tile.shape[-1] > sample_size or tile.shape[-2] > sample_size)
+                tile = sp_enc(tile) if big else enc_fn(tile)
+                row.append(tile[:, :, 1:] if i > 0 else tile)
+            return _stitch_t(row, bl, lt - bl)
+        if spatial and (x.shape[-1] > sample_size or x.shape[-2] > sample_size):
+            return sp_enc(x)
+        return enc_fn(x)
+
+    def decode(z):
+        if temporal and z.shape[2] > lt:
+            ov, bl = int(lt * (1 - overlap)), int(sample_tsize * overlap)
+            row = []
+            for i in range(0, z.shape[2], ov):
+                tile = z[:, :, i:i + lt + 1]
+                big = spatial and (tile.shape[-1] > ls or tile.shape[-2] > ls)
+                dec = sp_dec(tile) if big else dec_fn(tile)
+                row.append(dec[:, :, 1:] if i > 0 else dec)
+            return _stitch_t(row, bl, sample_tsize - bl)
+        if spatial and (z.shape[-1] > ls or z.shape[-2] > ls):
+            return sp_dec(z)
+        return dec_fn(z)
+
+    return encode, decode

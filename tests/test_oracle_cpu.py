@@ -202,3 +202,19 @@ def test_mmdit_full_model_matches_reference():
     out = M.model_forward(_w("model"), cfg, G["model_img"], G["ids"][:, Lt:], G["model_txt"], G["ids"][:, :Lt],
                           G["model_t"], G["model_y"], cond=G["model_cond"], guidance=G["model_g"])
     torch.testing.assert_close(out, G["model_out"], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("tag,sp,tp", [("none", False, False), ("spatial", True, False), ("temporal", False, True), ("both", True, True)])
+def test_tiled_autoencoder_matches_reference(tag, sp, tp):
+    """autoencoder_kl_causal_3d.py:269-358,384-552 executed by the reference (tests/golden/make_golden_vae_tiled.py)."""
+    GT = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(HERE, "golden", "vae_tiled.npz")).items()}
+    down, up = V.stage_plan(4, 4, 8)
+    We, Wd = _wv("enc"), _wv("dec")
+    enc_fn = lambda x: V.causal_conv3d(V.encoder(We, x, groups=4, strides=down), GT["quant_w"], GT["quant_b"])  # noqa: E731
+    dec_fn = lambda z: V.decoder(Wd, V.causal_conv3d(z, GT["post_w"], GT["post_b"]), groups=4, factors=up)      # noqa: E731
+    encode, decode = V.tiled_autoencoder(enc_fn, dec_fn, sample_size=32, sample_tsize=8, spatial=sp, temporal=tp)
+    moments = encode(GT["x"])
+    z = 0.476986 * moments[:, :4]   # posterior.mode() then scale_factor * (z - shift_factor), :304-311
+    torch.testing.assert_close(z, GT[f"z_{tag}"], rtol=1e-3, atol=1e-3)
+    y = decode(GT[f"z_{tag}"] / 0.476986)
+    torch.testing.assert_close(y, GT[f"y_{tag}"], rtol=2e-3, atol=2e-3)

@@ -179,3 +179,42 @@ def test_conv_causality_on_gpu(osb):
     x2[:, -1] += 1.0
     y1 = m(x2)
     assert torch.equal(y0[:, :-1], y1[:, :-1]) and not torch.equal(y0[:, -1], y1[:, -1])
+
+
+@pytest.mark.parametrize("tag,sp,tp", [("none", False, False), ("spatial", True, False), ("temporal", False, True), ("both", True, True)])
+def test_tiled_modes_against_reference_goldens(osb, tag, sp, tp):
+    """Tiled / blended encode + decode (autoencoder_kl_causal_3d.py:384-552) vs the reference class executed in fp32
+    (tests/golden/vae_tiled.npz); tolerance = the reference arithmetic itself in bf16 (noise floor) x 1.5."""
+    from opensora.registry import MODELS, build_module
+    from oracle import vae_oracle as V
+    from tests.util import rel_l2
+
+    G = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(HERE, "golden", "vae_blocks.npz")).items()}
+    GT = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(HERE, "golden", "vae_tiled.npz")).items()}
+    m = build_module(dict(type="hunyuan_vae", block_out_channels=(16, 32, 32, 32), layers_per_block=1, norm_num_groups=4,
+                          latent_channels=4, sample_size=32, sample_tsize=8, use_spatial_tiling=sp, use_temporal_tiling=tp),
+                     MODELS, device_map="cpu")
+    m.encoder.load_state_dict({k[4:]: v for k, v in G.items() if k.startswith("enc.")})
+    m.decoder.load_state_dict({k[4:]: v for k, v in G.items() if k.startswith("dec.")})
+    with torch.no_grad():
+        m.quant_conv.weight.copy_(GT["quant_w"]); m.quant_conv.bias.copy_(GT["quant_b"])
+        m.post_quant_conv.weight.copy_(GT["post_w"]); m.post_quant_conv.bias.copy_(GT["post_b"])
+    m = m.cuda().to(torch.bfloat16)
+    with torch.no_grad():
+        z = m.encode(GT["x"].cuda(), sample_posterior=False)
+        y = m.decode(GT[f"z_{tag}"].cuda())
+    # noise floor: oracle (restated reference) in bf16
+    down, up = V.stage_plan(4, 4, 8)
+    bf = lambda d, pfx: {k[len(pfx):]: v.cuda().to(torch.bfloat16) for k, v in d.items() if k.startswith(pfx)}  # noqa: E731
+    We, Wd = bf(G, "enc."), bf(G, "dec.")
+    qw, qb, pw, pb = (GT[k].cuda().to(torch.bfloat16) for k in ("quant_w", "quant_b", "post_w", "post_b"))
+    encode, decode = V.tiled_autoencoder(lambda x: V.causal_conv3d(V.encoder(We, x, groups=4, strides=down), qw, qb),
+                                         lambda t: V.decoder(Wd, V.causal_conv3d(t, pw, pb), groups=4, factors=up),
+                                         sample_size=32, sample_tsize=8, spatial=sp, temporal=tp)
+    zf = rel_l2(0.476986 * encode(GT["x"].cuda().to(torch.bfloat16))[:, :4], GT[f"z_{tag}"].cuda())
+    yf = rel_l2(decode((GT[f"z_{tag}"].cuda() / 0.476986).to(torch.bfloat16)), GT[f"y_{tag}"].cuda())
+    rz, _ = report(f"tiled encode [{tag}]", z, GT[f"z_{tag}"].cuda())
+    ry, _ = report(f"tiled decode [{tag}]", y, GT[f"y_{tag}"].cuda())
+    print(f"[parity] reference-in-bf16 noise floor: encode {zf:.3e} decode {yf:.3e}")
+    assert z.shape == GT[f"z_{tag}"].shape and y.shape == GT[f"y_{tag}"].shape
+    assert rz < max(1.5 * zf, 1e-2) and ry < max(1.5 * yf, 1e-2)
