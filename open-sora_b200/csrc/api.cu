@@ -3,6 +3,8 @@
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 
+#include <stdlib.h>
+
 #include <atomic>
 
 #include "common.cuh"
@@ -23,6 +25,10 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 bool initialised() { return g_init; }
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("OSB_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 int sm_count() { return g_sms; }
 
 int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,

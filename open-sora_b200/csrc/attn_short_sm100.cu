@@ -214,9 +214,9 @@ __global__ void __launch_bounds__(kAttnThreads, (D <= 72) ? 2 : 1) attn_short_ke
   uint8_t* sP = smem + p.off_p;        // ceil(NKP/64) chunks of [128 x 64]
   float* xch = reinterpret_cast<float*>(smem + p.off_misc);          // [2][128] pair exchange (ss / max)
   float* xsum = xch + 256;                                           // [2][128] partial row sums
-  float* xqn = xch + 512;                                            // [2][128] partial |q|^2 of the staged rows
-  uint32_t* kmax2 = reinterpret_cast<uint32_t*>(xch + 768);          // max |k|^2 over the staged keys (float bits)
-  const uint32_t bar_s = smem_u32(smem + p.off_misc + 3200);
+  float* xqn = xsum;   // [2][128] partial |q|^2 of the staged rows: read before the max-exchange barrier, xsum written after it
+  uint32_t* kmax2 = reinterpret_cast<uint32_t*>(xch + 512);          // max |k|^2 over the staged keys (float bits)
+  const uint32_t bar_s = smem_u32(smem + p.off_misc + 2056);
   const uint32_t bar_o = bar_s + 8;
   const uint32_t tmem_slot = bar_s + 16;
   const int k_chunk_bytes = p.NKP * 128;
@@ -250,6 +250,30 @@ __global__ void __launch_bounds__(kAttnThreads, (D <= 72) ? 2 : 1) attn_short_ke
     qt_begin = (unit % p.groups_per_seq) * p.QT;
     qt_end = qt_begin + p.QT < p.tiles_per_seq ? qt_begin + p.QT : p.tiles_per_seq;
   }
+
+  pdl_wait();  // barrier init / TMEM allocation above overlapped the previous kernel; q, k, v are visible from here
+  pdl_launch_dependents();  // the next kernel may set up on SMs as our CTAs retire (its own pdl_wait orders the data)
+  // ---- Q rows are prefetched into registers one q-tile ahead: the first tile's loads fly during the K / V staging,
+  //      the next tile's during the current tile's softmax (saves one exposed DRAM round trip per tile) ----------
+  const int pf_ub = part == 0 ? 0 : U0;
+  const int pf_ue = part == 0 ? U0 : U;
+  uint4 tq[U0];
+  auto prefetch_q = [&](int qt) {
+    const int g_ = (p.G > 1) ? r / p.Lq : 0;
+    const int tok_ = (p.G > 1) ? r - g_ * p.Lq : qt * 128 + r;
+    const int64_t seq_ = seq0 + g_;
+#pragma unroll
+    for (int i = 0; i < U0; ++i) tq[i] = make_uint4(0, 0, 0, 0);
+    if ((g_ < p.G) && (seq_ < p.num_seqs) && (tok_ < p.Lq)) {
+      const int64_t b = seq_ / p.seqs_per_batch, j = seq_ % p.seqs_per_batch;
+      const int64_t row_ = b * p.q_bs + j * p.q_ss + (int64_t)tok_ * p.q_ts;
+      const uint4* qs = reinterpret_cast<const uint4*>(p.q + row_ * p.q_ld + (int64_t)h * D);
+#pragma unroll
+      for (int i = 0; i < U0; ++i)
+        if (pf_ub + i < pf_ue) tq[i] = __ldg(qs + pf_ub + i);
+    }
+  };
+  prefetch_q(qt_begin);
 
   // ---- stage K and V^T once -----------------------------------------------------------------
   for (int slot = tid; slot < p.NKP; slot += kAttnThreads) {
@@ -325,18 +349,10 @@ __global__ void __launch_bounds__(kAttnThreads, (D <= 72) ? 2 : 1) attn_short_ke
     }
     // ---- stage Q: the pair splits the row's units [0,U0) / [U0,UP) ------------------------------
     {
-      const int ub = part == 0 ? 0 : U0;
-      const int ue = part == 0 ? U0 : U;
       uint4 t[U0];
       float ss = 0.f;
 #pragma unroll
-      for (int i = 0; i < U0; ++i) t[i] = make_uint4(0, 0, 0, 0);
-      if (q_valid) {
-        const uint4* qs = reinterpret_cast<const uint4*>(p.q + q_row * p.q_ld + (int64_t)h * D);
-#pragma unroll
-        for (int i = 0; i < U0; ++i)
-          if (ub + i < ue) t[i] = __ldg(qs + ub + i);
-      }
+      for (int i = 0; i < U0; ++i) t[i] = tq[i];   // prefetched one tile ahead
       float rq = 1.f;
       if (p.qw != nullptr) {
 #pragma unroll
@@ -382,6 +398,7 @@ __global__ void __launch_bounds__(kAttnThreads, (D <= 72) ? 2 : 1) attn_short_ke
       }
       umma_commit<1>(bar_s);
     }
+    if (qt + 1 < qt_end) prefetch_q(qt + 1);
     mbar_wait(bar_s, par);
     tc_fence_after();
 
@@ -588,6 +605,8 @@ __global__ void __launch_bounds__(kFlashThreads, (D <= 72) ? 2 : 1) attn_flash_k
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  pdl_wait();
+  pdl_launch_dependents();
   // work item -> (sequence(s), q-tile range, head); consecutive items share a head (K/V of a head stay in L2)
   auto decode = [&](int64_t item, int64_t& seq0, int& qt0, int& qt1, int& h) {
     h = (int)(item / g.units);
@@ -930,8 +949,9 @@ static int attn_flash_launch(AttnParams& p, int H, cudaStream_t stream) {
   }
   g.items = g.units * H;
   int64_t grid = slots < g.items ? slots : g.items;
-  attn_flash_kernel<D, kPTmem><<<(unsigned)grid, kFlashThreads, smem, stream>>>(p, g);
-  OSB_CHECK_CUDA(cudaGetLastError());
+  cudaLaunchAttribute attr[2];
+  cudaLaunchConfig_t cfg = launch_config(dim3((unsigned)grid), dim3(kFlashThreads), smem, stream, attr);
+  OSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn_flash_kernel<D, kPTmem>, p, g));
   count_launch();
   return OSB_OK;
 }
@@ -948,7 +968,7 @@ static int attn_launch(AttnParams& p, int64_t units, int H, cudaStream_t stream)
   p.off_kt = off; off += up1k(Cfg::TAIL ? p.NKP * 32 : 0);
   p.off_vt = off; off += up1k(nkc * Cfg::DP * 128);
   p.off_p = off; off += nkc * 128 * 128;
-  p.off_misc = off; off += 3200 + 64;
+  p.off_misc = off; off += 2056 + 32;
   const int smem = off;
   const int s_cols = (p.NKP + 31) / 32 * 32;
   p.o_col = s_cols;
@@ -958,8 +978,9 @@ static int attn_launch(AttnParams& p, int64_t units, int H, cudaStream_t stream)
     return OSB_ERR_UNSUPPORTED;
   }
   dim3 grid((unsigned)units, (unsigned)H);
-  attn_short_kernel<D><<<grid, kAttnThreads, smem, stream>>>(p);
-  OSB_CHECK_CUDA(cudaGetLastError());
+  cudaLaunchAttribute attr[2];
+  cudaLaunchConfig_t cfg = launch_config(grid, dim3(kAttnThreads), smem, stream, attr);
+  OSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn_short_kernel<D>, p));
   count_launch();
   return OSB_OK;
 }

@@ -40,6 +40,34 @@ int sm_count();
 
 // Encode a 2D tiled tensor map over a row-major bf16 matrix [rows, cols] with row stride `ld`
 // elements; box = box_rows x box_cols, 128-byte swizzle (box_cols must be 64), zero OOB fill.
+// Launch configuration shared by every kernel: grid / block / smem / stream + the PDL attribute (and an optional
+// cluster dimension).  `attrs` must have room for 2 entries and outlive the launch call.
+bool pdl_enabled();
+inline cudaLaunchConfig_t launch_config(dim3 grid, dim3 block, size_t smem, cudaStream_t stream, cudaLaunchAttribute* attrs,
+                                        unsigned cluster_x = 1) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    attrs[n].id = cudaLaunchAttributeClusterDimension;
+    attrs[n].val.clusterDim.x = cluster_x;
+    attrs[n].val.clusterDim.y = 1;
+    attrs[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attrs;
+  cfg.numAttrs = n;
+  return cfg;
+}
+
 int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t ld, uint32_t box_rows, uint32_t box_cols);
 
@@ -144,6 +172,14 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;"
                ::: "memory");
 }
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// Every osb200 kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization (osb::launch_config):
+// its prologue (barrier init, TMEM allocation, descriptor prefetch) may overlap the tail of the previous kernel in
+// the stream; pdl_wait() must precede the first access to memory the previous kernel may have written, and
+// pdl_launch_dependents() lets the next kernel's CTAs start filling SMs this kernel has already vacated.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- proxy fences ------------------------------------------------------------------------
 // make generic-proxy smem writes visible to the async proxy (TMA / tensor core operand reads)

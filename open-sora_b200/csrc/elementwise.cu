@@ -18,6 +18,8 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
                    int64_t group_rows, const int32_t* __restrict__ mod_index, int64_t mod_stride, float eps) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kLnWarpsPerBlock + (threadIdx.x >> 5);
+  pdl_wait();
+  pdl_launch_dependents();
   if (row >= rows) return;
   const int nchunks = C >> 3;
   const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
@@ -113,9 +115,10 @@ extern "C" int osb_ln_modulate(const void* x, const float* shift, const float* s
   __nv_bfloat16* yb = static_cast<__nv_bfloat16*>(y);
 #define OSB_LN_CASE(N)                                                                               \
   if (nch <= N) {                                                                                    \
-    ln_modulate_kernel<N><<<blocks, kLnWarpsPerBlock * 32, 0, s>>>(xb, shift, scale, yb, rows, C,    \
-                                                                   group_rows, mod_index, mod_stride, eps); \
-    OSB_CHECK_CUDA(cudaGetLastError());                                                              \
+    cudaLaunchAttribute attr[2];                                                                     \
+    cudaLaunchConfig_t cfg = launch_config(dim3(blocks), dim3(kLnWarpsPerBlock * 32), 0, s, attr);   \
+    OSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ln_modulate_kernel<N>, xb, shift, scale, yb, rows, C,    \
+                                      group_rows, mod_index, mod_stride, eps));                      \
     count_launch();                                                                                  \
     return OSB_OK;                                                                                   \
   }
@@ -139,6 +142,7 @@ __global__ void __launch_bounds__(256)
 cfg_euler_kernel(const uint4* __restrict__ c, const uint4* __restrict__ u, const uint4* __restrict__ u2,
                  const uint4* __restrict__ x, uint4* __restrict__ out, int64_t nvec, float g_txt, float g_img,
                  const uint4* __restrict__ g_map, int64_t map_vecs, float dt) {
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const uint4 cv = c[i], uv = u[i], xv = x[i];
     const uint4 u2v = u2 ? u2[i] : uv;

@@ -146,6 +146,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
     // ===================== TMA producer (A and W tiles) =====================
@@ -188,6 +189,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
+      pdl_launch_dependents();  // this CTA has issued all its loads: dependents may start filling vacated SMs
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA) =====================
@@ -388,18 +390,8 @@ static int launch_kernel(const CUtensorMap& ta, const CUtensorMap& tw, const CUt
   using Cfg = GemmCfg<BLOCK_N, kCta, kRes>;
   int64_t clusters = sm_count() / kCta;
   if (tiles < clusters) clusters = tiles;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(clusters * kCta));
-  cfg.blockDim = dim3(kNumThreads);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCta;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cudaLaunchAttribute attr[2];
+  cudaLaunchConfig_t cfg = launch_config(dim3((unsigned)(clusters * kCta)), dim3(kNumThreads), Cfg::SMEM_BYTES, stream, attr, kCta);
   OSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BLOCK_N, kCta, kRes, kConv>, ta, tw, tr, p, cg));
   count_launch();
   return OSB_OK;

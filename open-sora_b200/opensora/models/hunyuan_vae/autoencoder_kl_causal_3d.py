@@ -118,13 +118,29 @@ class AutoencoderKLCausal3D(nn.Module):
     def _to_ncdhw(x):
         return x.permute(0, 4, 1, 2, 3).contiguous()
 
+    @staticmethod
+    def _pointwise(osb, x2d, conv):
+        """1x1x1 Conv3d == GEMM over channels-last rows.  osb_gemm_bf16 wants K, N multiples of 8: narrower (test-sized)
+        latent widths are zero-padded on both sides; the production widths (16 / 32) take the direct path."""
+        C = conv.weight.shape[0]
+        w, b = conv.weight.reshape(C, C), conv.bias
+        if C % 8 == 0:
+            return osb.gemm(x2d, w, b)
+        Cp = (C + 7) // 8 * 8
+        wp = torch.zeros(Cp, Cp, dtype=w.dtype, device=w.device)
+        wp[:C, :C] = w
+        bp = torch.zeros(Cp, dtype=b.dtype, device=b.device)
+        bp[:C] = b
+        xp = torch.nn.functional.pad(x2d, (0, Cp - C))
+        return osb.gemm(xp, wp, bp)[:, :C].contiguous()
+
     # ---- tile-level building blocks (NCDHW in / out, bf16) ----------------------------------------------------
     def _encode_moments(self, x):
         """encoder + quant_conv on one (tile of a) video -> moments [B, 2*latent, T', h, w]."""
         osb = self._check()
         h = self.encoder(self._to_ndhwc(x, cpad=8))
         nb, T, H, W, C2 = h.shape
-        m = osb.gemm(h.reshape(-1, C2), self.quant_conv.weight.reshape(C2, C2), self.quant_conv.bias)
+        m = self._pointwise(osb, h.reshape(-1, C2), self.quant_conv)
         return self._to_ncdhw(m.view(nb, T, H, W, C2))
 
     def _decode_tile(self, z):
@@ -132,7 +148,7 @@ class AutoencoderKLCausal3D(nn.Module):
         osb = self._check()
         zl = self._to_ndhwc(z)
         nb, T, H, W, C = zl.shape
-        zl = osb.gemm(zl.reshape(-1, C), self.post_quant_conv.weight.reshape(C, C), self.post_quant_conv.bias)
+        zl = self._pointwise(osb, zl.reshape(-1, C), self.post_quant_conv)
         return self._to_ncdhw(self.decoder(zl.view(nb, T, H, W, C)))
 
     @staticmethod
