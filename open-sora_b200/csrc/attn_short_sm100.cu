@@ -16,6 +16,8 @@
 //
 // Replaces: opensora/models/mmdit/math.py:22-36 (attention), layers.py:102-135 (QK RMSNorm) and the
 // upstream-v1.2 STDiT3 Attention / MultiHeadCrossAttention restated in SURVEY.md App. A.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace osb {
@@ -956,6 +958,698 @@ static int attn_flash_launch(AttnParams& p, int H, cudaStream_t stream) {
   return OSB_OK;
 }
 
+// One head row that cp.async has already placed in its K-major operand tile: optional RMSNorm scale and interleaved
+// RoPE, in place.  Two sweeps over shared memory (sum of squares, then one 16-byte unit at a time) instead of holding
+// the row in registers: the loader warps run with a small register budget so that many of them fit next to the
+// softmax warpgroups.  Returns the squared length of the finished vector (before bf16 rounding).
+template <int D>
+__device__ __forceinline__ float finish_row_inplace(uint8_t* main_base, int main_chunk_bytes, uint8_t* tail_base, int row,
+                                                    const __nv_bfloat16* w, float eps, const float* cosr, const float* sinr) {
+  using Cfg = AttnCfg<D>;
+  auto unit_ptr = [&](int u) -> uint4* {
+    return (u < Cfg::MAIN * 8) ? reinterpret_cast<uint4*>(main_base + (u >> 3) * main_chunk_bytes + sw128_off(row, u & 7))
+                               : reinterpret_cast<uint4*>(tail_base + tail_off(row, u - Cfg::MAIN * 8));
+  };
+  float ss0 = 0.f, ss1 = 0.f;
+#pragma unroll
+  for (int u = 0; u < Cfg::U; ++u) { const float q = sumsq8(*unit_ptr(u)); if (u & 1) ss1 += q; else ss0 += q; }
+  const float ss = ss0 + ss1;
+  if (w == nullptr && cosr == nullptr) return ss;
+  const float r = (w != nullptr) ? rsqrtf(ss * (1.0f / D) + eps) : 1.f;
+  float n0 = 0.f, n1 = 0.f;
+#pragma unroll
+  for (int u = 0; u < Cfg::U; ++u) {
+    uint4* ptr = unit_ptr(u);
+    float xu[8];
+    unpack8(*ptr, xu);
+    if (w != nullptr) {
+      float wf[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(w) + u), wf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) xu[e] *= r * wf[e];
+    }
+    float q = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) q += xu[e] * xu[e];
+    if (u & 1) n1 += q; else n0 += q;
+    if (cosr != nullptr) {
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(cosr) + u);
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(sinr) + u);
+      const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float a = xu[2 * i], b = xu[2 * i + 1];
+        xu[2 * i] = a * cc[i] - b * sn[i];
+        xu[2 * i + 1] = b * cc[i] + a * sn[i];
+      }
+    }
+    *ptr = pack8(xu);
+  }
+  return n0 + n1;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Ping-pong kernel for resident key sets (<= 2 blocks of <= 160 keys): STDiT3 spatial / temporal / T5 cross attention.
+//
+// One CTA per SM walks a contiguous range of "jobs" (one 128-row q-tile against its key set).  Consecutive jobs
+// alternate between two slots; each slot has its own Q tile in shared memory, its own S/P and O accumulators in TMEM
+// and its own softmax warpgroup, so the tensor pipe works on one slot's S = Q K^T / O += P V while the other slot's
+// warpgroup is in its exp2 pass (the MUFU-bound part).  Key sets (K, V blocks) live in a ring of stages shared by both
+// slots: the two q-tiles of a spatial sequence and the 128 q-tiles of a cross-attention head reuse one staged set.
+//
+// Loads are register-free: the loader warps (one group for Q tiles, one for K/V blocks) issue cp.async (16 B, zero-fill for padding rows) straight into the final
+// swizzled operand position, one task ahead of the one being finished; rows that need RMSNorm / RoPE are then read
+// back by their owner thread, transformed in fp32 and written in place.  V (and q/k without norm) are pure copies.
+// ------------------------------------------------------------------------------------------------------------------
+#ifdef OSB_PP_TRACE
+// debug build only (tests/pp_trace.py): CTA 0 records (tag, clock64) per role: 0/1 softmax slots, 2 loader, 3 issuer
+__device__ unsigned long long g_pp_trace[4][512];
+__device__ int g_pp_trace_n[4];
+#define PP_TR(role, tag)                                                                              \
+  do {                                                                                                \
+    if (blockIdx.x == 0) {                                                                            \
+      const int n_ = g_pp_trace_n[role];                                                              \
+      if (n_ < 256) { g_pp_trace[role][2 * n_] = (tag); g_pp_trace[role][2 * n_ + 1] = clock64(); g_pp_trace_n[role] = n_ + 1; } \
+    }                                                                                                 \
+  } while (0)
+#else
+#define PP_TR(role, tag) do { } while (0)
+#endif
+constexpr int kPPThreads = 800;   // warps 0-3 / 4-7 softmax of slot 0 / 1, 8-11 / 12-15 Q loaders of slot 0 / 1,
+constexpr int kPPIssuerWarp = 24;   // 16-23 K/V loaders, 24 tcgen05 issuer (25 warps: 80 registers per thread; the
+constexpr int kPPKvThreads = 256;   // row transforms are latency bound, so they get thread-level parallelism)
+constexpr int kPPKvWarps = kPPKvThreads / 32;
+constexpr int kPPMaxStages = 4;
+
+struct PPGeom {
+  int32_t BK, NKB, NSETS;        // keys per block (multiple of 16, <= 160), blocks per key set, key sets in the ring
+  int32_t q_bytes, qt_off;       // per-slot Q buffer size; offset of its head-dim tail tile
+  int32_t k_bytes, kt_bytes;     // per stage: K main, K tail (V main / tail have the same sizes)
+  int32_t stage_bytes, off_kv, off_bar;
+  int32_t s_cols, o_col, o_cols; // TMEM: slot s has S/P at s * s_cols and O at o_col + s * o_cols
+  int32_t tps;                   // jobs (q-tiles) per key set
+  int64_t units;                 // key sets per head
+  int64_t num_sets;              // units * heads
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;   // src-size 0: the 16 destination bytes are zero-filled, nothing is read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int D>
+__global__ void __launch_bounds__(kPPThreads, 1) attn_pp_kernel(const AttnParams p, const PPGeom g) {
+  using Cfg = AttnCfg<D>;
+  constexpr int U = Cfg::U;
+  constexpr int NMAIN = Cfg::MAIN * 64;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  auto sQ = [&](int s) { return smem + s * g.q_bytes; };
+  auto sQt = [&](int s) { return smem + s * g.q_bytes + g.qt_off; };
+  auto sK = [&](int st) { return smem + g.off_kv + st * g.stage_bytes; };
+  auto sKt = [&](int st) { return smem + g.off_kv + st * g.stage_bytes + g.k_bytes; };
+  auto sV = [&](int st) { return smem + g.off_kv + st * g.stage_bytes + g.k_bytes + g.kt_bytes; };
+  auto sVt = [&](int st) { return smem + g.off_kv + st * g.stage_bytes + 2 * g.k_bytes + g.kt_bytes; };
+  const uint32_t bar0 = smem_u32(smem + g.off_bar);
+  auto q_full = [&](int s) { return bar0 + 8u * s; };
+  auto q_empty = [&](int s) { return bar0 + 16u + 8u * s; };
+  auto s_full = [&](int s) { return bar0 + 32u + 8u * s; };
+  auto p_full = [&](int s) { return bar0 + 48u + 8u * s; };
+  auto o_full = [&](int s) { return bar0 + 64u + 8u * s; };
+  auto kv_full = [&](int st) { return bar0 + 80u + 8u * st; };
+  auto kv_empty = [&](int st) { return bar0 + 112u + 8u * st; };
+  const uint32_t tmem_slot = bar0 + 144u;
+  // squared lengths of the staged (normalised) vectors: |q_row|^2 per slot and row, max |k_row|^2 per stage and loader
+  // warp.  |q||k| bounds every logit of the row (Cauchy-Schwarz), which lets the softmax skip its max pass.
+  float* qn2 = reinterpret_cast<float*>(smem + g.off_bar + 256);       // [2 slots][2 (job parity)][128]
+  float* kmax2 = qn2 + 512;                                              // [kPPMaxStages][kPPKvWarps]
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == kPPIssuerWarp) {
+    if ((tid & 31) == 0) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(q_full(s), 128); mbar_init(q_empty(s), 1); mbar_init(s_full(s), 1); mbar_init(p_full(s), 128);
+        mbar_init(o_full(s), 1);
+      }
+      for (int st = 0; st < kPPMaxStages; ++st) { mbar_init(kv_full(st), kPPKvThreads); mbar_init(kv_empty(st), 1); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<1>(tmem_slot, 512u);
+  }
+  if (Cfg::TAIL) {
+    // head-dim tail tiles: the zero-pad unit (columns D..DP-1) is written once here; copies only ever fill unit 0
+    const int nst = g.NSETS * g.NKB;
+    for (int i = tid; i < 2 * 256; i += kPPThreads)   // two Q tail tiles of 128 rows x 32 B
+      *reinterpret_cast<uint4*>(sQt(i >> 8) + (i & 255) * 16) = make_uint4(0, 0, 0, 0);
+    const int units_t = g.kt_bytes / 16;
+    for (int i = tid; i < nst * 2 * units_t; i += kPPThreads) {
+      const int st = i / (2 * units_t), rem = i - st * 2 * units_t;
+      uint8_t* base = rem < units_t ? sKt(st) : sVt(st);
+      *reinterpret_cast<uint4*>(base + (rem % units_t) * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  pdl_wait();
+  pdl_launch_dependents();
+
+  // ---- this CTA's contiguous job range; jobs of one key set are never split when a set has few q-tiles ----------
+  int64_t J0, J1;
+  if (g.tps <= 4) {
+    J0 = ((int64_t)blockIdx.x * g.num_sets / gridDim.x) * g.tps;
+    J1 = ((int64_t)(blockIdx.x + 1) * g.num_sets / gridDim.x) * g.tps;
+  } else {
+    const int64_t total = g.num_sets * g.tps;
+    J0 = (int64_t)blockIdx.x * total / gridDim.x;
+    J1 = (int64_t)(blockIdx.x + 1) * total / gridDim.x;
+  }
+  const int nj = (int)(J1 - J0);
+  auto decode = [&](int64_t J, int64_t& seq0, int& qt, int& h) {
+    const int64_t set = J / g.tps;
+    qt = (int)(J - set * g.tps);
+    h = (int)(set / g.units);
+    const int64_t unit = set - (int64_t)h * g.units;
+    seq0 = (p.G > 1) ? unit * p.G : unit;
+  };
+  auto first_of_set = [&](int i) { return i == 0 || ((J0 + i) % g.tps) == 0; };
+  auto last_of_set = [&](int i) { return i == nj - 1 || ((J0 + i + 1) % g.tps) == 0; };
+
+  if (warp < 8) {
+    // ============================ softmax / correction / epilogue of one slot ============================
+    const int slot = warp >> 2;
+    const int r = tid & 127;
+    const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t t_s = t_row + (uint32_t)(slot * g.s_cols);
+    const uint32_t t_o = t_row + (uint32_t)(g.o_col + slot * g.o_cols);
+    const int nch = g.BK >> 4;   // 16-column chunks (BK is a multiple of 16)
+    uint32_t n_s = 0, n_o = 0;
+    int64_t set_ord = -1;
+    for (int i = 0; i < nj; ++i) {
+      if (first_of_set(i)) ++set_ord;
+      if ((i & 1) != slot) continue;
+      int64_t seq0; int qt, h;
+      decode(J0 + i, seq0, qt, h);
+      const int grp = (p.G > 1) ? r / p.Lq : 0;
+      const int qtok = (p.G > 1) ? r - grp * p.Lq : qt * 128 + r;
+      const int64_t qseq = seq0 + grp;
+      const bool q_valid = (grp < p.G) && (qseq < p.num_seqs) && (qtok < p.Lq);
+      int64_t q_row = 0;
+      int key_lo = 0x7fffffff, key_hi = 0;
+      if (q_valid) {
+        const int64_t b = qseq / p.seqs_per_batch, j = qseq % p.seqs_per_batch;
+        q_row = b * p.q_bs + j * p.q_ss + (int64_t)qtok * p.q_ts;
+        const int len = p.kv_lens ? p.kv_lens[qseq] : p.Lk;
+        key_lo = grp * p.Lk;
+        key_hi = key_lo + (len < p.Lk ? len : p.Lk);
+      }
+      // warp-wide key range: it guards the .sync.aligned TMEM loads (rows of one warp can belong to different packed
+      // sequences), the per-lane range only guards arithmetic
+      const int wkey_lo = __reduce_min_sync(0xffffffffu, key_lo), wkey_hi = __reduce_max_sync(0xffffffffu, key_hi);
+      float m = -INFINITY, l = 0.f, shift = 0.f;
+      bool onepass = false;
+      for (int jb = 0; jb < g.NKB; ++jb) {
+        const int k0 = jb * g.BK;
+        mbar_wait(s_full(slot), n_s & 1); ++n_s;
+        tc_fence_after();
+        if (r == 0) PP_TR(slot, 10);
+        if (jb == 0) {
+          // logit bound |q_r| * max|k| * scale (log2 domain): small enough -> it replaces the row maximum, exactly
+          // (softmax is shift invariant; 2^-2B stays a normal fp32 / bf16 number for B <= 60)
+          float km = 0.f;
+          const int st0 = (int)(set_ord % g.NSETS) * g.NKB;
+          for (int b2 = 0; b2 < g.NKB; ++b2) {
+#pragma unroll
+            for (int w4 = 0; w4 < kPPKvWarps / 4; ++w4) {
+              const float4 k4 = *reinterpret_cast<const float4*>(kmax2 + (st0 + b2) * kPPKvWarps + w4 * 4);
+              km = fmaxf(km, fmaxf(fmaxf(k4.x, k4.y), fmaxf(k4.z, k4.w)));
+            }
+          }
+          const float bound = sqrtf(qn2[(slot * 2 + ((i >> 1) & 1)) * 128 + r] * km) * fabsf(p.scale_log2);
+          onepass = !__any_sync(0xffffffffu, !(bound <= 60.f));
+          shift = bound;
+        }
+        if (onepass) {
+          // ---- single pass: P = exp2(S * scale - bound) and its row sum, 16 columns per TMEM load ----
+          const float ms = shift;
+          float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+          for (int c0 = 0; c0 < g.BK; c0 += 16) {
+            const int ka = k0 + c0;
+            uint32_t pk[8];
+            if (ka + 16 <= wkey_lo || ka >= wkey_hi) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) pk[j] = 0u;
+            } else {
+              uint32_t v[16];
+              tmem_ld_32x32b_x16(t_s + c0, v);
+              tmem_ld_wait();
+              if (ka >= key_lo && ka + 16 <= key_hi) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  const float e0 = fast_exp2(__uint_as_float(v[j]) * p.scale_log2 - ms);
+                  const float e1 = fast_exp2(__uint_as_float(v[j + 1]) * p.scale_log2 - ms);
+                  const float e2 = fast_exp2(__uint_as_float(v[j + 2]) * p.scale_log2 - ms);
+                  const float e3 = fast_exp2(__uint_as_float(v[j + 3]) * p.scale_log2 - ms);
+                  l0 += e0; l1 += e1; l2 += e2; l3 += e3;
+                  pk[j >> 1] = pack_bf16x2(e0, e1);
+                  pk[(j >> 1) + 1] = pack_bf16x2(e2, e3);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                  const bool ok0 = ka + j >= key_lo && ka + j < key_hi;
+                  const bool ok1 = ka + j + 1 >= key_lo && ka + j + 1 < key_hi;
+                  const float e0 = ok0 ? fast_exp2(__uint_as_float(v[j]) * p.scale_log2 - ms) : 0.f;
+                  const float e1 = ok1 ? fast_exp2(__uint_as_float(v[j + 1]) * p.scale_log2 - ms) : 0.f;
+                  l0 += e0; l1 += e1;
+                  pk[j >> 1] = pack_bf16x2(e0, e1);
+                }
+              }
+            }
+            tmem_st_32x32b_x8(t_s + (c0 >> 1), pk);
+          }
+          l += (l0 + l1) + (l2 + l3);
+          // stay in lockstep with the P V of the previous block (no rescale needed): a waiter may lag an mbarrier by at
+          // most one phase, or its parity test aliases to the phase after next
+          if (jb > 0) { mbar_wait(o_full(slot), n_o & 1); ++n_o; }
+        } else {
+          // ---- two passes with an online maximum (logit bound too large to be used as the shift) ----
+          auto active = [&](int c) { const int ka = k0 + c * 16; return !(ka + 16 <= wkey_lo || ka >= wkey_hi); };
+          auto full = [&](int c) { const int ka = k0 + c * 16; return ka >= key_lo && ka + 16 <= key_hi; };
+          uint32_t va[16], vb[16];
+          float mb0 = -INFINITY, mb1 = -INFINITY, mb2 = -INFINITY, mb3 = -INFINITY;
+          auto max_chunk = [&](const uint32_t (&v)[16], int c) {
+            if (full(c)) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                mb0 = fmaxf(mb0, __uint_as_float(v[j])); mb1 = fmaxf(mb1, __uint_as_float(v[j + 1]));
+                mb2 = fmaxf(mb2, __uint_as_float(v[j + 2])); mb3 = fmaxf(mb3, __uint_as_float(v[j + 3]));
+              }
+            } else {
+              const int ka = k0 + c * 16;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (ka + j >= key_lo && ka + j < key_hi) mb0 = fmaxf(mb0, __uint_as_float(v[j]));
+            }
+          };
+          if (active(0)) tmem_ld_32x32b_x16(t_s, va);
+          tmem_ld_wait();
+          for (int c = 0; c < nch; c += 2) {
+            if (c + 1 < nch && active(c + 1)) tmem_ld_32x32b_x16(t_s + (c + 1) * 16, vb);
+            if (active(c)) max_chunk(va, c);
+            tmem_ld_wait();
+            if (c + 1 < nch) {
+              if (c + 2 < nch && active(c + 2)) tmem_ld_32x32b_x16(t_s + (c + 2) * 16, va);
+              if (active(c + 1)) max_chunk(vb, c + 1);
+              tmem_ld_wait();
+            }
+          }
+          const float m_new = fmaxf(m, fmaxf(fmaxf(mb0, mb1), fmaxf(mb2, mb3)));
+          const float ms = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
+          if (jb > 0) {   // rescale the running O / l when the maximum grew (the previous P V must have landed)
+            mbar_wait(o_full(slot), n_o & 1); ++n_o;
+            tc_fence_after();
+            const float alpha = (m == -INFINITY) ? 1.f : fast_exp2(m * p.scale_log2 - ms);
+            if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll 1
+              for (int c = 0; c < Cfg::DP; c += 16) {
+                uint32_t o[16];
+                tmem_ld_32x32b_x16(t_o + c, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                tmem_st_32x32b_x16(t_o + c, o);
+              }
+              tmem_st_wait();
+            }
+            l *= alpha;
+          }
+          float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+          auto exp_chunk = [&](const uint32_t (&v)[16], int c) {
+            uint32_t pk[8];
+            if (!active(c)) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) pk[j] = 0u;
+            } else if (full(c)) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float e0 = fast_exp2(__uint_as_float(v[j]) * p.scale_log2 - ms);
+                const float e1 = fast_exp2(__uint_as_float(v[j + 1]) * p.scale_log2 - ms);
+                const float e2 = fast_exp2(__uint_as_float(v[j + 2]) * p.scale_log2 - ms);
+                const float e3 = fast_exp2(__uint_as_float(v[j + 3]) * p.scale_log2 - ms);
+                l0 += e0; l1 += e1; l2 += e2; l3 += e3;
+                pk[j >> 1] = pack_bf16x2(e0, e1);
+                pk[(j >> 1) + 1] = pack_bf16x2(e2, e3);
+              }
+            } else {
+              const int ka = k0 + c * 16;
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                const bool ok0 = ka + j >= key_lo && ka + j < key_hi;
+                const bool ok1 = ka + j + 1 >= key_lo && ka + j + 1 < key_hi;
+                const float e0 = ok0 ? fast_exp2(__uint_as_float(v[j]) * p.scale_log2 - ms) : 0.f;
+                const float e1 = ok1 ? fast_exp2(__uint_as_float(v[j + 1]) * p.scale_log2 - ms) : 0.f;
+                l0 += e0; l1 += e1;
+                pk[j >> 1] = pack_bf16x2(e0, e1);
+              }
+            }
+            tmem_st_32x32b_x8(t_s + c * 8, pk);
+          };
+          if (active(0)) tmem_ld_32x32b_x16(t_s, va);
+          tmem_ld_wait();
+          for (int c = 0; c < nch; c += 2) {
+            if (c + 1 < nch && active(c + 1)) tmem_ld_32x32b_x16(t_s + (c + 1) * 16, vb);
+            exp_chunk(va, c);
+            tmem_ld_wait();
+            if (c + 1 < nch) {
+              if (c + 2 < nch && active(c + 2)) tmem_ld_32x32b_x16(t_s + (c + 2) * 16, va);
+              exp_chunk(vb, c + 1);
+              tmem_ld_wait();
+            }
+          }
+          l += (l0 + l1) + (l2 + l3);
+          m = m_new;
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_full(slot));
+        if (r == 0) PP_TR(slot, 13);
+      }
+      // ---- epilogue: wait for the last P V ----
+      mbar_wait(o_full(slot), n_o & 1); ++n_o;
+      tc_fence_after();
+      if (r == 0) PP_TR(slot, 14);
+      const float inv = l > 0.f ? 1.0f / l : 0.f;
+      __nv_bfloat16* orow = p.out + q_row * p.out_ld + (int64_t)h * D;
+      {
+        // O row: MAIN*64 + tail columns, read in 16-column pieces
+        uint32_t v[16];
+#pragma unroll
+        for (int c = 0; c < Cfg::MAIN * 64; c += 16) {
+          tmem_ld_32x32b_x16(t_o + c, v);
+          tmem_ld_wait();
+          if (q_valid) {
+#pragma unroll
+            for (int u2 = 0; u2 < 2; ++u2) {
+              float o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[u2 * 8 + e]) * inv;
+              *reinterpret_cast<uint4*>(orow + c + u2 * 8) = pack8(o);
+            }
+          }
+        }
+        if (Cfg::TAIL) {
+          uint32_t w8[8];
+          tmem_ld_32x32b_x8(t_o + Cfg::MAIN * 64, w8);
+          tmem_ld_wait();
+          if (q_valid) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(w8[e]) * inv;
+            *reinterpret_cast<uint4*>(orow + Cfg::MAIN * 64) = pack8(o);
+          }
+        }
+      }
+      if (r == 0) PP_TR(slot, 15);
+      tc_fence_before();  // this slot's O / S are overwritten by MMAs issued only after our next p_full arrival
+    }
+  } else if (warp < 16) {
+    // ============================ Q loaders: warps 8-11 stage slot 0's tiles, warps 12-15 slot 1's ============================
+    const int slot = (warp - 8) >> 2;
+    const int lt = tid - 256 - slot * 128;   // tile row
+    uint32_t n_fill = 0;
+    for (int i = slot; i < nj; i += 2) {
+      int64_t seq0; int qt, h;
+      decode(J0 + i, seq0, qt, h);
+      const int grp = (p.G > 1) ? lt / p.Lq : 0;
+      const int qtok = (p.G > 1) ? lt - grp * p.Lq : qt * 128 + lt;
+      const int64_t qseq = seq0 + grp;
+      const bool ok = (grp < p.G) && (qseq < p.num_seqs) && (qtok < p.Lq);
+      const __nv_bfloat16* src = p.q;
+      if (ok) {
+        const int64_t b = qseq / p.seqs_per_batch, j = qseq % p.seqs_per_batch;
+        src = p.q + (b * p.q_bs + j * p.q_ss + (int64_t)qtok * p.q_ts) * p.q_ld + (int64_t)h * D;
+      }
+      mbar_wait(q_empty(slot), (n_fill & 1) ^ 1); ++n_fill;   // the previous tile's S MMAs are done with this buffer
+      const uint32_t mb = smem_u32(sQ(slot)), tb = smem_u32(sQt(slot));
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t dst = (u < Cfg::MAIN * 8) ? mb + (u >> 3) * (128 * 128) + sw128_off(lt, u & 7)
+                                                 : tb + tail_off(lt, u - Cfg::MAIN * 8);
+        cp_async16(dst, src + (ok ? u * 8 : 0), ok);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+      if (lt == 0) PP_TR(2, 23);
+      const __nv_bfloat16* qwt = (p.qw2 != nullptr && qtok >= p.norm_split) ? p.qw2 : p.qw;
+      const int ctok = ok ? qtok : 0;   // padding rows: any valid table row (their values are zero)
+      const float nrm2 = finish_row_inplace<D>(sQ(slot), 128 * 128, sQt(slot), lt, qwt, p.eps,
+                                               p.cos ? p.cos + (int64_t)ctok * (D / 2) : nullptr,
+                                               p.sin ? p.sin + (int64_t)ctok * (D / 2) : nullptr);
+      // (double-buffered: with one key block per job the slot's next tile may be staged while this one's softmax starts)
+      qn2[(slot * 2 + ((i >> 1) & 1)) * 128 + lt] = nrm2 * 1.02f;   // margin for the bf16 rounding of the staged values
+      fence_proxy_async_smem();
+      mbar_arrive(q_full(slot));
+      if (lt == 0) PP_TR(2, 24);
+    }
+  } else if (warp < kPPIssuerWarp) {
+    // ============================ K / V loaders: one task per key set (all its blocks) ============================
+    const int lt = tid - 512;
+    struct KTask { int ring, h; int64_t seq0; };
+    int ki = 0;
+    int64_t kord = -1;
+    auto next_task = [&](KTask& t) -> bool {
+      while (ki < nj && !first_of_set(ki)) ++ki;
+      if (ki >= nj) return false;
+      ++kord;
+      int qt;
+      decode(J0 + ki, t.seq0, qt, t.h);
+      t.ring = (int)(kord % g.NSETS);
+      ++ki;
+      return true;
+    };
+    uint32_t n_fill[kPPMaxStages] = {0, 0, 0, 0};
+    const int rows_set = g.NKB * g.BK;
+    auto issue = [&](const KTask& t, bool blocking) -> bool {
+      for (int jb = 0; jb < g.NKB; ++jb) {
+        const int st = t.ring * g.NKB + jb;
+        const uint32_t par = (n_fill[st] & 1) ^ 1;
+        if (blocking) mbar_wait(kv_empty(st), par);
+        else if (!mbar_test_wait(kv_empty(st), par)) return false;
+      }
+      for (int jb = 0; jb < g.NKB; ++jb) ++n_fill[t.ring * g.NKB + jb];
+      for (int rs = lt; rs < rows_set; rs += kPPKvThreads) {
+        const int jb = rs / g.BK, row = rs - jb * g.BK;
+        const int st = t.ring * g.NKB + jb;
+        const uint32_t kb = smem_u32(sK(st)), ktb = smem_u32(sKt(st));
+        const uint32_t vb = smem_u32(sV(st)), vtb = smem_u32(sVt(st));
+        const int kg = rs / p.Lk, ktok = rs - kg * p.Lk;
+        const int64_t kseq = t.seq0 + kg;
+        const bool ok = (rs < p.NK) && (kseq < p.num_seqs);
+        const __nv_bfloat16 *ks = p.k, *vs = p.v;
+        if (ok) {
+          const int64_t b = kseq / p.seqs_per_batch, j = kseq % p.seqs_per_batch;
+          const int64_t k_row = b * p.k_bs + j * p.k_ss + (int64_t)ktok * p.k_ts;
+          ks = p.k + k_row * p.k_ld + (int64_t)t.h * D;
+          vs = p.v + k_row * p.v_ld + (int64_t)t.h * D;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const bool main = u < Cfg::MAIN * 8;
+          const uint32_t offm = (u >> 3) * (uint32_t)(g.BK * 128) + sw128_off(row, u & 7);
+          const uint32_t offt = tail_off(row, u - Cfg::MAIN * 8);
+          cp_async16(main ? kb + offm : ktb + offt, ks + (ok ? u * 8 : 0), ok);
+          cp_async16(main ? vb + offm : vtb + offt, vs + (ok ? u * 8 : 0), ok);
+        }
+      }
+      cp_async_commit();
+      return true;
+    };
+    auto finish = [&](const KTask& t) {
+      float kmx[2] = {0.f, 0.f};   // this thread's max |k_row|^2 per block
+      for (int rs = lt; rs < rows_set; rs += kPPKvThreads) {
+        const int jb = rs / g.BK, row = rs - jb * g.BK;
+        const int st = t.ring * g.NKB + jb;
+        const int kg = rs / p.Lk;
+        const int ktok = rs - kg * p.Lk;
+        const __nv_bfloat16* kwt = (p.kw2 != nullptr && ktok >= p.norm_split) ? p.kw2 : p.kw;
+        const float nrm2 = finish_row_inplace<D>(sK(st), g.BK * 128, sKt(st), row, kwt, p.eps,
+                                                 p.cos ? p.cos + (int64_t)ktok * (D / 2) : nullptr,
+                                                 p.sin ? p.sin + (int64_t)ktok * (D / 2) : nullptr);
+        if (jb == 0) kmx[0] = fmaxf(kmx[0], nrm2); else kmx[1] = fmaxf(kmx[1], nrm2);
+      }
+      for (int jb = 0; jb < g.NKB; ++jb) {
+        float v = (jb == 0 ? kmx[0] : kmx[1]) * 1.02f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if ((lt & 31) == 0) kmax2[(t.ring * g.NKB + jb) * kPPKvWarps + (lt >> 5)] = v;
+      }
+      fence_proxy_async_smem();
+      for (int jb = 0; jb < g.NKB; ++jb) mbar_arrive(kv_full(t.ring * g.NKB + jb));
+    };
+    KTask cur, nxt;
+    bool have_cur = next_task(cur);
+    if (have_cur) issue(cur, true);
+    while (have_cur) {
+      const bool have_nxt = next_task(nxt);
+      const bool early = have_nxt && issue(nxt, false);   // per lane: a lane that could not start early issues after finish()
+      if (early) cp_async_wait<1>(); else cp_async_wait<0>();
+      if (lt == 0) PP_TR(2, 31);
+      finish(cur);
+      if (lt == 0) PP_TR(2, 32);
+      if (have_nxt && !early) issue(nxt, true);
+      cur = nxt;
+      have_cur = have_nxt;
+    }
+  } else {
+    // ============================ tcgen05 issuer ============================
+    // The whole warp runs the control flow (barrier waits, descriptor arithmetic stay warp-uniform, so operands live
+    // in uniform registers); one elected lane issues the tcgen05 instructions.
+    const bool leader = elect_one();
+    uint32_t n_q[2] = {0, 0}, n_p[2] = {0, 0}, n_kv[kPPMaxStages] = {0, 0, 0, 0};
+    const uint32_t idesc_s = make_idesc_bf16_f32(128, g.BK);
+    const uint32_t idesc_om = make_idesc_bf16_f32_bmn(128, NMAIN);
+    const uint32_t idesc_ot = make_idesc_bf16_f32_bmn(128, 16);
+    const uint32_t kchunk16 = (uint32_t)(g.BK * 128) >> 4;   // K main chunk stride in descriptor (16 B) units
+    const int steps = g.BK / 16;
+    int64_t set_ord = -1;
+    int set_slot[2] = {0, 0};     // ring position of the key set each slot's current job uses
+    bool set_first[2] = {false, false}, set_last[2] = {false, false};
+    auto issue_s = [&](int s, int jb) {
+      const int st = set_slot[s] * g.NKB + jb;
+      if (set_first[s]) { mbar_wait(kv_full(st), n_kv[st] & 1); ++n_kv[st]; }
+      tc_fence_after();
+      const uint32_t d = tmem_base + (uint32_t)(s * g.s_cols);
+      // descriptors advance by constant address steps: built once per S, bumped per MMA
+      const uint64_t qd0 = make_sw128_kmajor_desc(smem_u32(sQ(s)));
+      const uint64_t kd0 = make_sw128_kmajor_desc(smem_u32(sK(st)));
+      const uint64_t qt0 = make_noswz_kmajor_desc(smem_u32(sQt(s)));
+      const uint64_t kt0 = make_noswz_kmajor_desc(smem_u32(sKt(st)));
+      if (leader) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int kc = 0; kc < Cfg::MAIN; ++kc) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            umma_bf16<1>(d, qd0 + (uint64_t)(kc * ((128 * 128) >> 4) + ks * 2), kd0 + (uint64_t)(kc * kchunk16 + ks * 2), idesc_s, acc);
+            acc = 1;
+          }
+        }
+        if (Cfg::TAIL) umma_bf16<1>(d, qt0, kt0, idesc_s, acc);
+        umma_commit<1>(s_full(s));
+        if (jb == g.NKB - 1) umma_commit<1>(q_empty(s));   // this slot's Q tile may be overwritten
+      }
+      __syncwarp();
+      if (leader) PP_TR(3, 44 + s);
+    };
+    auto start = [&](int s, int i) {   // bind job i to slot s and issue its first S
+      set_first[s] = first_of_set(i);
+      set_last[s] = last_of_set(i);
+      if (set_first[s]) ++set_ord;
+      set_slot[s] = (int)(set_ord % g.NSETS);
+      mbar_wait(q_full(s), n_q[s] & 1); ++n_q[s];
+      if (leader) PP_TR(3, 40 + s);
+      issue_s(s, 0);
+    };
+    auto step = [&](int s, int jb) {   // O (+)= P V of key block jb, then the S of the next block
+      const int st = set_slot[s] * g.NKB + jb;
+      mbar_wait(p_full(s), n_p[s] & 1); ++n_p[s];
+      tc_fence_after();
+      if (leader) PP_TR(3, 46 + s);
+      const uint32_t d_o = tmem_base + (uint32_t)(g.o_col + s * g.o_cols);
+      const uint32_t a_p = tmem_base + (uint32_t)(s * g.s_cols);
+      const uint64_t vd0 = make_sw128_mnmajor_desc(smem_u32(sV(st)), (uint32_t)(g.BK * 128));
+      const uint64_t vt0 = make_noswz_mnmajor_desc(smem_u32(sVt(st)));
+      const uint32_t acc0 = jb > 0 ? 1u : 0u;
+      if (leader) {
+        // per 16 keys: one MMA over the swizzled main chunk(s) (N = 64 / 128), one over the head-dim tail (N = 16)
+        umma_bf16_ts(d_o, a_p, vd0, idesc_om, acc0);
+        if (Cfg::TAIL) umma_bf16_ts(d_o + NMAIN, a_p, vt0, idesc_ot, acc0);
+#pragma unroll 3
+        for (int k = 1; k < steps; ++k) {
+          umma_bf16_ts(d_o, a_p + k * 8, vd0 + (uint64_t)(k * (2048 >> 4)), idesc_om, 1u);
+          if (Cfg::TAIL) umma_bf16_ts(d_o + NMAIN, a_p + k * 8, vt0 + (uint64_t)(k * (512 >> 4)), idesc_ot, 1u);
+        }
+        if (set_last[s] && jb == g.NKB - 1)   // every reader of this key set has been issued: free its stages
+          for (int b2 = 0; b2 < g.NKB; ++b2) umma_commit<1>(kv_empty(set_slot[s] * g.NKB + b2));
+        umma_commit<1>(o_full(s));
+      }
+      __syncwarp();
+      if (leader) PP_TR(3, 48 + s);
+      if (jb + 1 < g.NKB) issue_s(s, jb + 1);
+    };
+    for (int jp = 0; jp < nj; jp += 2) {
+      const int ns = (nj - jp) < 2 ? (nj - jp) : 2;
+      // With a single ring position, a new key set can only be staged after the previous set's last P V: a pair that
+      // straddles the boundary runs its two jobs one after the other (happens once per head in cross attention).
+      const bool serial = ns == 2 && g.NSETS == 1 && first_of_set(jp + 1);
+      if (serial) {
+        start(0, jp);
+        for (int jb = 0; jb < g.NKB; ++jb) step(0, jb);
+        start(1, jp + 1);
+        for (int jb = 0; jb < g.NKB; ++jb) step(1, jb);
+      } else {
+        for (int s = 0; s < ns; ++s) start(s, jp + s);
+        for (int jb = 0; jb < g.NKB; ++jb)
+          for (int s = 0; s < ns; ++s) step(s, jb);
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kPPIssuerWarp) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512u);
+  }
+}
+
+// eligibility + geometry of the ping-pong kernel; returns OSB_ERR_UNSUPPORTED (without setting an error) when the
+// shape belongs to the other kernels
+template <int D>
+static int attn_pp_launch(AttnParams& p, int H, cudaStream_t stream) {
+  using Cfg = AttnCfg<D>;
+  PPGeom g = {};
+  auto up1k = [](int x) { return (x + 1023) / 1024 * 1024; };
+  g.NKB = p.NK > 160 ? 2 : 1;
+  g.BK = (((p.NK + g.NKB - 1) / g.NKB) + 15) / 16 * 16;
+  if (p.NK > 320 || g.BK > 160 || p.rope_half) return OSB_ERR_UNSUPPORTED;
+  g.qt_off = Cfg::MAIN * 128 * 128;
+  g.q_bytes = g.qt_off + up1k(Cfg::TAIL ? 128 * 32 : 0);
+  g.k_bytes = up1k(Cfg::MAIN * g.BK * 128);
+  g.kt_bytes = up1k(Cfg::TAIL ? g.BK * 32 : 0);
+  g.stage_bytes = 2 * (g.k_bytes + g.kt_bytes);
+  g.off_kv = 2 * g.q_bytes;
+  const int budget = 227 * 1024 - g.off_kv - 256 - 4 * 128 * 4 - kPPMaxStages * kPPKvWarps * 4;
+  int nst = budget / g.stage_bytes;
+  if (nst > kPPMaxStages) nst = kPPMaxStages;
+  g.NSETS = nst / g.NKB;
+  if (g.NSETS < 1) return OSB_ERR_UNSUPPORTED;
+  g.off_bar = g.off_kv + g.NSETS * g.NKB * g.stage_bytes;
+  const int smem = g.off_bar + 256 + 4 * 128 * 4 + kPPMaxStages * kPPKvWarps * 4;
+  g.s_cols = (g.BK + 31) / 32 * 32;
+  g.o_cols = Cfg::DP;
+  g.o_col = 2 * g.s_cols;
+  if (g.o_col + 2 * g.o_cols > 512) return OSB_ERR_UNSUPPORTED;
+  g.tps = (p.G > 1) ? 1 : p.tiles_per_seq;
+  g.units = (p.G > 1) ? (p.num_seqs + p.G - 1) / p.G : p.num_seqs;
+  g.num_sets = g.units * H;
+  const int64_t work = (g.tps <= 4) ? g.num_sets : g.num_sets * g.tps;
+  const int64_t grid = work < sm_count() ? work : sm_count();
+  cudaLaunchAttribute attr[2];
+  cudaLaunchConfig_t cfg = launch_config(dim3((unsigned)grid), dim3(kPPThreads), smem, stream, attr);
+  OSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn_pp_kernel<D>, p, g));
+  count_launch();
+  return OSB_OK;
+}
+
 template <int D>
 static int attn_launch(AttnParams& p, int64_t units, int H, cudaStream_t stream) {
   using Cfg = AttnCfg<D>;
@@ -985,6 +1679,12 @@ static int attn_launch(AttnParams& p, int64_t units, int H, cudaStream_t stream)
   return OSB_OK;
 }
 
+// OSB_ATTN_PP=0/1: let the default dispatch use the ping-pong kernel for two-block resident key sets
+bool pp_auto() {
+  static const bool on = [] { const char* e = getenv("OSB_ATTN_PP"); return e != nullptr && e[0] == '1'; }();
+  return on;
+}
+
 int attn_init() {
   OSB_CHECK_CUDA(cudaFuncSetAttribute(attn_short_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   OSB_CHECK_CUDA(cudaFuncSetAttribute(attn_short_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -995,10 +1695,21 @@ int attn_init() {
   OSB_CHECK_CUDA(cudaFuncSetAttribute(attn_flash_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   OSB_CHECK_CUDA(cudaFuncSetAttribute(attn_flash_kernel<72, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   OSB_CHECK_CUDA(cudaFuncSetAttribute(attn_flash_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  OSB_CHECK_CUDA(cudaFuncSetAttribute(attn_pp_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  OSB_CHECK_CUDA(cudaFuncSetAttribute(attn_pp_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   return OSB_OK;
 }
 
 }  // namespace osb
+
+#ifdef OSB_PP_TRACE
+extern "C" int osb_debug_pp_trace(unsigned long long* dst, int* counts) {
+  int zero[4] = {0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(dst, osb::g_pp_trace, sizeof(unsigned long long) * 4 * 512) != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(counts, osb::g_pp_trace_n, sizeof(int) * 4) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(osb::g_pp_trace_n, zero, sizeof(zero)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" int osb_attn_short(const osb_attn_short_args* a, void* stream) {
   using namespace osb;
@@ -1075,10 +1786,19 @@ extern "C" int osb_attn_short(const osb_attn_short_args* a, void* stream) {
   p.NKP = (p.NK + 15) / 16 * 16;
   // implementation: reserved = 1 resident-key kernel, 2 flash (P through smem), 3 flash (P in TMEM), 0 = default
   int impl = a->reserved;
+  if (impl == 0 && pp_auto() && D <= 72 && !p.rope_half && p.NK > 160 && p.NK <= 320) impl = 4;   // two resident key blocks
   if (impl == 0) {
     // measured on B200 (profiles/r01_attn_v4.log): the flash kernel with P in TMEM wins when two key blocks are
     // resident and two CTAs fit an SM (STDiT3 spatial: 128 vs 153 us); the one-pass resident kernel wins for a
     // single block (temporal) and for 3 resident blocks at one CTA per SM (T5 cross: 117 vs 209 us)
+    const int nkb = (p.NK + 127) / 128;
+    impl = (p.NK > kMaxKeys) ? 3 : ((nkb == 2 && D <= 72) ? 3 : 1);
+  }
+  if (impl == 4) {   // ping-pong kernel (resident key sets, head_dim <= 72); other shapes keep the default choice
+    int rc = OSB_ERR_UNSUPPORTED;
+    if (D == 64) rc = attn_pp_launch<64>(p, a->num_heads, static_cast<cudaStream_t>(stream));
+    else if (D == 72) rc = attn_pp_launch<72>(p, a->num_heads, static_cast<cudaStream_t>(stream));
+    if (rc != OSB_ERR_UNSUPPORTED) return rc;
     const int nkb = (p.NK + 127) / 128;
     impl = (p.NK > kMaxKeys) ? 3 : ((nkb == 2 && D <= 72) ? 3 : 1);
   }

@@ -93,6 +93,7 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
   }
 }
 
+
 }  // namespace osb
 
 extern "C" int osb_ln_modulate(const void* x, const float* shift, const float* scale, void* y,

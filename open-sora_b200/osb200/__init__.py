@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libosb200.so")
+LIB_PATH = os.environ.get("OSB200_LIB", os.path.join(_HERE, "libosb200.so"))  # override: instrumented debug builds
 
 # every symbol include/osb200.h declares (tests check the library exports all of them)
 EXPORTS = (

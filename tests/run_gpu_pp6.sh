@@ -1,0 +1,21 @@
+#!/bin/bash
+# ping-pong attention v3 + streaming LN: parity first, timing only if parity is green (a hang costs GPU minutes)
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "attn or ln_modulate" > gpurun_out/pp6_pytest.log 2>&1; rc=$?; echo "pytest attn+ln rc=$rc"
+grep -E "passed|failed|^FAILED|^ERROR|timed out" gpurun_out/pp6_pytest.log | tail -n 8
+[ $rc -ne 0 ] && exit 0
+timeout 90 python tests/attn_prof.py 0 4 > gpurun_out/attn_prof_pp6.log 2>&1; rc=$?; echo "attn_prof rc=$rc"; grep -E "attn impl|timed out" gpurun_out/attn_prof_pp6.log | head -n 8
+[ $rc -ne 0 ] && exit 0
+OSB_ATTN_IMPL=4 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-vae > gpurun_out/bench_pp6.json 2> gpurun_out/bench_pp6.err; echo "bench pp rc=$?"
+python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/bench_pp6.json").read().strip().splitlines()[-1])
+    print("pp value",round(d["value"],2),"ms",round(d["ms_per_step"],2),"e2e",round(d["e2e"]["value"],2), d["roofline"]["families"])
+except Exception as e: print("no json", e)
+PY
+timeout 90 python tests/pp_trace.py 130 > gpurun_out/pp_trace6.log 2>&1; echo "trace rc=$?"
+grep "===" gpurun_out/pp_trace6.log
+OSB_ATTN_IMPL=4 timeout 300 python -m pytest tests/test_stdit3_gpu.py -m gpu -q -x > gpurun_out/pp6_stdit3.log 2>&1; echo "stdit3 impl4 rc=$?"
+grep -E "passed|failed|timed out" gpurun_out/pp6_stdit3.log | head -n 5

@@ -28,7 +28,8 @@ def _randn(*shape, scale=1.0, seed=0):
 
 
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("rows,C,group_rows", [(1000, 1152, 250), (77, 3072, 77), (4096, 384, 1024), (9, 64, 3)])
+@pytest.mark.parametrize("rows,C,group_rows", [(1000, 1152, 250), (77, 3072, 77), (4096, 384, 1024), (9, 64, 3),
+                                                (4099, 1152, 4099), (16384, 1152, 8192)])
 def test_ln_modulate(osb, rows, C, group_rows):
     x = _randn(rows, C, seed=1) * 3 + 0.5
     G = (rows + group_rows - 1) // group_rows
@@ -178,7 +179,7 @@ def _rope_tables(L, D):
     return ang.cos().contiguous(), ang.sin().contiguous()
 
 
-IMPLS = [1, 2, 3]  # resident keys, flash with P through smem, flash with P in TMEM
+IMPLS = [1, 2, 3, 4]  # resident keys, flash with P through smem, flash with P in TMEM, two-slot ping-pong
 
 
 @pytest.mark.parametrize("impl", IMPLS)
@@ -231,6 +232,81 @@ def test_attn_cross(osb, Ly, impl):
     ref = ref.permute(0, 2, 1, 3).reshape(B * N, C)
     r, _ = report(f"attn cross Ly{Ly} impl{impl}", out, ref)
     assert r < 4e-3
+
+
+@pytest.mark.parametrize("impl", [1, 3, 4])
+@pytest.mark.parametrize("T,S", [(4, 24), (3, 40), (5, 7)])
+def test_attn_packed_ragged(osb, T, S, impl):
+    """Short sequences packed G per 128-row tile where G*L < 128 and rows of one warp belong to different sequences
+    (XS parity shapes: S=24 -> G=5): block-diagonal masking must not make warp-collective TMEM accesses diverge."""
+    B, H, D = 2, 4, 72
+    C, N = H * D, T * S
+    qkv = _randn(B * N, 3 * C, seed=41)
+    qw, kw = _randn(D, seed=42) * 0.2 + 1, _randn(D, seed=43) * 0.2 + 1
+    q2, k2, v2 = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    for mode in ("spatial", "temporal"):
+        out = torch.zeros(B * N, C, dtype=torch.bfloat16, device="cuda")
+        if mode == "spatial":
+            st = (N, S, 1)
+            osb.attn_short(q2, k2, v2, out, num_seqs=B * T, seqs_per_batch=T, q_strides=st, k_strides=st, Lq=S, Lk=S,
+                           num_heads=H, head_dim=D, q_norm_w=qw, k_norm_w=kw, impl=impl)
+            x = qkv.float().view(B * T, S, 3, H, D).permute(2, 0, 3, 1, 4)
+            ref = _attn_ref(x[0], x[1], x[2], qw, kw, None, None, D ** -0.5).permute(0, 2, 1, 3).reshape(B * N, C)
+        else:
+            cos, sin = _rope_tables(T, D)
+            st = (N, 1, S)
+            osb.attn_short(q2, k2, v2, out, num_seqs=B * S, seqs_per_batch=S, q_strides=st, k_strides=st, Lq=T, Lk=T,
+                           num_heads=H, head_dim=D, q_norm_w=qw, k_norm_w=kw, rope_cos=cos, rope_sin=sin, impl=impl)
+            x = qkv.float().view(B, T, S, 3, H, D).permute(3, 0, 2, 4, 1, 5).reshape(3, B * S, H, T, D)
+            ref = _attn_ref(x[0], x[1], x[2], qw, kw, cos, sin, D ** -0.5)
+            ref = ref.view(B, S, H, T, D).permute(0, 3, 1, 2, 4).reshape(B * N, C)
+        r, _ = report(f"attn packed ragged {mode} T{T} S{S} impl{impl}", out, ref)
+        assert r < 4e-3
+
+
+@pytest.mark.parametrize("big_logits", [False, True])
+@pytest.mark.parametrize("mode", ["spatial", "temporal", "cross"])
+def test_attn_pingpong_many_sets(osb, mode, big_logits):
+    """The two-slot kernel when every CTA walks several key sets: ring reuse of the K/V stages, jobs of one set split
+    between CTAs (cross: 41 q-tiles per head over 148 CTAs), odd job counts.  big_logits scales q / the norm weights so
+    that the Cauchy-Schwarz logit bound exceeds the one-pass limit and the two-pass (online max) path runs."""
+    H, D = 4, 72
+    C = H * D
+    amp = 6.0 if big_logits else 1.0   # bound ~ 12 * amp log2-units; the one-pass limit is 60
+    if mode == "cross":
+        B, N, Ly = 2, 128 * 41 - 50, 300
+        q = _randn(B * N, C, seed=31) * amp
+        kv = _randn(B * Ly, 2 * C, seed=32)
+        lens = torch.tensor([260, 300], device="cuda", dtype=torch.int32)
+        out = torch.zeros(B * N, C, dtype=torch.bfloat16, device="cuda")
+        osb.attn_short(q, kv[:, :C], kv[:, C:], out, num_seqs=B, seqs_per_batch=1, q_strides=(N, 0, 1),
+                       k_strides=(Ly, 0, 1), Lq=N, Lk=Ly, num_heads=H, head_dim=D, kv_lens=lens, impl=4)
+        qf = q.float().view(B, N, H, D).permute(0, 2, 1, 3)
+        kvf = kv.float().view(B, Ly, 2, H, D).permute(2, 0, 3, 1, 4)
+        ref = _attn_ref(qf, kvf[0], kvf[1], None, None, None, None, D ** -0.5, kv_len=lens).permute(0, 2, 1, 3).reshape(B * N, C)
+    else:
+        B, T, S = (1, 331, 256) if mode == "spatial" else (1, 64, 1307)
+        N = T * S
+        qkv = _randn(B * N, 3 * C, seed=33)
+        qw, kw = (_randn(D, seed=34) * 0.2 + 1) * amp, _randn(D, seed=35) * 0.2 + 1
+        out = torch.zeros(B * N, C, dtype=torch.bfloat16, device="cuda")
+        q2, k2, v2 = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+        if mode == "spatial":
+            st = (N, S, 1)
+            osb.attn_short(q2, k2, v2, out, num_seqs=B * T, seqs_per_batch=T, q_strides=st, k_strides=st, Lq=S, Lk=S,
+                           num_heads=H, head_dim=D, q_norm_w=qw, k_norm_w=kw, impl=4)
+            x = qkv.float().view(B * T, S, 3, H, D).permute(2, 0, 3, 1, 4)
+            ref = _attn_ref(x[0], x[1], x[2], qw, kw, None, None, D ** -0.5).permute(0, 2, 1, 3).reshape(B * N, C)
+        else:
+            cos, sin = _rope_tables(T, D)
+            st = (N, 1, S)
+            osb.attn_short(q2, k2, v2, out, num_seqs=B * S, seqs_per_batch=S, q_strides=st, k_strides=st, Lq=T, Lk=T,
+                           num_heads=H, head_dim=D, q_norm_w=qw, k_norm_w=kw, rope_cos=cos, rope_sin=sin, impl=4)
+            x = qkv.float().view(B, T, S, 3, H, D).permute(3, 0, 2, 4, 1, 5).reshape(3, B * S, H, T, D)
+            ref = _attn_ref(x[0], x[1], x[2], qw, kw, cos, sin, D ** -0.5)
+            ref = ref.view(B, S, H, T, D).permute(0, 3, 1, 2, 4).reshape(B * N, C)
+    r, _ = report(f"attn ping-pong many sets {mode} big_logits={big_logits}", out, ref)
+    assert r < (2e-2 if big_logits else 4e-3)   # large logits amplify the bf16 rounding of q-hat / k-hat themselves
 
 
 @pytest.mark.parametrize("impl", [2, 3])
