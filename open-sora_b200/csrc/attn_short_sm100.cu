@@ -377,28 +377,31 @@ __global__ void __launch_bounds__(kAttnThreads, (D <= 72) ? 2 : 1) attn_short_ke
     tc_fence_after();
 
     // ---- S = Q K^T ----------------------------------------------------------------------------
-    if (tid == 0) {
-      for (int n0 = 0; n0 < p.NKP; n0 += 256) {
-        const int n = (p.NKP - n0) < 256 ? (p.NKP - n0) : 256;
-        const uint32_t idesc = make_idesc_bf16_f32(128, n);
-        uint32_t acc = 0;
+    // (warp 0 computes the descriptors warp-uniformly and one elected lane issues: operands stay in uniform registers
+    // and the MMAs go out back to back instead of one uniformisation loop per instruction)
+    if (warp == 0) {
+      const uint64_t qd0 = make_sw128_kmajor_desc(smem_u32(sQ)), kd0 = make_sw128_kmajor_desc(smem_u32(sK));
+      const uint64_t qtd = make_noswz_kmajor_desc(smem_u32(sQt)), ktd = make_noswz_kmajor_desc(smem_u32(sKt));
+      const uint32_t kchunk16 = (uint32_t)k_chunk_bytes >> 4;
+      if (elect_one()) {
+        for (int n0 = 0; n0 < p.NKP; n0 += 256) {
+          const int n = (p.NKP - n0) < 256 ? (p.NKP - n0) : 256;
+          const uint32_t idesc = make_idesc_bf16_f32(128, n);
+          uint32_t acc = 0;
 #pragma unroll
-        for (int kc = 0; kc < Cfg::MAIN; ++kc) {
+          for (int kc = 0; kc < Cfg::MAIN; ++kc) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t da = make_sw128_kmajor_desc(smem_u32(sQ) + kc * (128 * 128) + ks * 32);
-            const uint64_t db = make_sw128_kmajor_desc(smem_u32(sK) + kc * k_chunk_bytes + n0 * 128 + ks * 32);
-            umma_bf16<1>(tmem_base + n0, da, db, idesc, acc);
-            acc = 1;
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_bf16<1>(tmem_base + n0, qd0 + (uint64_t)(kc * ((128 * 128) >> 4) + ks * 2),
+                           kd0 + (uint64_t)(kc * kchunk16 + n0 * (128 >> 4) + ks * 2), idesc, acc);
+              acc = 1;
+            }
           }
+          if (Cfg::TAIL) umma_bf16<1>(tmem_base + n0, qtd, ktd + (uint64_t)((n0 >> 3) * (256 >> 4)), idesc, acc);
         }
-        if (Cfg::TAIL) {
-          const uint64_t da = make_noswz_kmajor_desc(smem_u32(sQt));
-          const uint64_t db = make_noswz_kmajor_desc(smem_u32(sKt) + (n0 >> 3) * 256);
-          umma_bf16<1>(tmem_base + n0, da, db, idesc, acc);
-        }
+        umma_commit<1>(bar_s);
       }
-      umma_commit<1>(bar_s);
+      __syncwarp();
     }
     if (qt + 1 < qt_end) prefetch_q(qt + 1);
     mbar_wait(bar_s, par);
@@ -481,16 +484,20 @@ __global__ void __launch_bounds__(kAttnThreads, (D <= 72) ? 2 : 1) attn_short_ke
     tc_fence_after();
 
     // ---- O = P V ---------------------------------------------------------------------------------
-    if (tid == 0) {
+    if (warp == 0) {
+      const uint64_t pd0 = make_sw128_kmajor_desc(smem_u32(sP)), vd0 = make_sw128_kmajor_desc(smem_u32(sVt));
+      const uint32_t vchunk16 = (uint32_t)vt_chunk_bytes >> 4;
       const uint32_t idesc = make_idesc_bf16_f32(128, DP);
       const int steps = p.NKP / 16;
-      for (int s = 0; s < steps; ++s) {
-        const int c = s >> 2, ks = s & 3;
-        const uint64_t da = make_sw128_kmajor_desc(smem_u32(sP) + c * (128 * 128) + ks * 32);
-        const uint64_t db = make_sw128_kmajor_desc(smem_u32(sVt) + c * vt_chunk_bytes + ks * 32);
-        umma_bf16<1>(tmem_base + p.o_col, da, db, idesc, s > 0 ? 1u : 0u);
+      if (elect_one()) {
+        for (int s = 0; s < steps; ++s) {
+          const int c = s >> 2, ks = s & 3;
+          umma_bf16<1>(tmem_base + p.o_col, pd0 + (uint64_t)(c * ((128 * 128) >> 4) + ks * 2),
+                       vd0 + (uint64_t)(c * vchunk16 + ks * 2), idesc, s > 0 ? 1u : 0u);
+        }
+        umma_commit<1>(bar_o);
       }
-      umma_commit<1>(bar_o);
+      __syncwarp();
     }
     const float tot = xsum[r] + xsum[128 + r];
     const float inv = tot > 0.f ? 1.0f / tot : 0.f;
@@ -839,11 +846,16 @@ __global__ void __launch_bounds__(kFlashThreads, (D <= 72) ? 2 : 1) attn_flash_k
     }
   } else {
     // ============================ tcgen05 issuer ============================
-    if ((tid & 31) == 0) {
+    // the whole warp runs the control flow (waits / descriptor arithmetic warp-uniform: operands in uniform registers,
+    // MMAs issue back to back); one elected lane issues
+    {
+      const bool leader = elect_one();
       uint32_t n_q = 0, n_p = 0, n_kv[3] = {0, 0, 0};
       const uint32_t idesc_s = make_idesc_bf16_f32(128, g.BK);
       const uint32_t idesc_om = make_idesc_bf16_f32_bmn(128, NMAIN);
       const uint32_t idesc_ot = make_idesc_bf16_f32_bmn(128, 16);
+      const uint32_t kchunk16 = (uint32_t)(g.BK * 128) >> 4;
+      const int steps = g.BK / 16;
       for (int64_t item = blockIdx.x; item < g.items; item += gridDim.x) {
         int64_t seq0; int qt0, qt1, h;
         decode(item, seq0, qt0, qt1, h);
@@ -854,40 +866,49 @@ __global__ void __launch_bounds__(kFlashThreads, (D <= 72) ? 2 : 1) attn_flash_k
             if (!g.resident || qt == qt0) { mbar_wait(kv_full(st), n_kv[st] & 1); ++n_kv[st]; }
             tc_fence_after();
             // S = Q K^T  (overwrites the S/P region: ordered after the previous PV by the in-order MMA pipe)
-            uint32_t acc = 0;
+            const uint64_t qd0 = make_sw128_kmajor_desc(smem_u32(sQ)), kd0 = make_sw128_kmajor_desc(smem_u32(sK(st)));
+            const uint64_t qt0d = make_noswz_kmajor_desc(smem_u32(sQt)), kt0d = make_noswz_kmajor_desc(smem_u32(sKt(st)));
+            if (leader) {
+              uint32_t acc = 0;
 #pragma unroll
-            for (int kc = 0; kc < Cfg::MAIN; ++kc) {
+              for (int kc = 0; kc < Cfg::MAIN; ++kc) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                umma_bf16<1>(tmem_base, make_sw128_kmajor_desc(smem_u32(sQ) + kc * (128 * 128) + ks * 32),
-                             make_sw128_kmajor_desc(smem_u32(sK(st)) + kc * (g.BK * 128) + ks * 32), idesc_s, acc);
-                acc = 1;
+                for (int ks = 0; ks < 4; ++ks) {
+                  umma_bf16<1>(tmem_base, qd0 + (uint64_t)(kc * ((128 * 128) >> 4) + ks * 2), kd0 + (uint64_t)(kc * kchunk16 + ks * 2),
+                               idesc_s, acc);
+                  acc = 1;
+                }
               }
+              if (Cfg::TAIL) umma_bf16<1>(tmem_base, qt0d, kt0d, idesc_s, acc);
+              umma_commit<1>(s_full);
+              if (jb == g.NKB - 1) umma_commit<1>(q_empty);   // sQ may be restaged for the next q-tile
             }
-            if (Cfg::TAIL)
-              umma_bf16<1>(tmem_base, make_noswz_kmajor_desc(smem_u32(sQt)), make_noswz_kmajor_desc(smem_u32(sKt(st))), idesc_s, acc);
-            umma_commit<1>(s_full);
-            if (jb == g.NKB - 1) umma_commit<1>(q_empty);   // sQ may be restaged for the next q-tile
+            __syncwarp();
             mbar_wait(p_full, n_p & 1); ++n_p;
             tc_fence_after();
             // O (+)= P V : per 16 keys, one MMA over the swizzled main chunk(s) (N = 64 / 128) and one over the
             // no-swizzle head-dim tail (N = 16); V is read as an MN-major operand (no transposition anywhere)
-            const int steps = g.BK / 16;
-            for (int s = 0; s < steps; ++s) {
-              const uint32_t accu = (jb > 0 || s > 0) ? 1u : 0u;
-              const uint64_t dbm = make_sw128_mnmajor_desc(smem_u32(sV(st)) + s * 2048, (uint32_t)(g.BK * 128));
-              const uint64_t dbt = make_noswz_mnmajor_desc(smem_u32(sVt(st)) + s * 512);
-              if constexpr (kPTmem) {
-                umma_bf16_ts(tmem_base + g.o_col, tmem_base + s * 8, dbm, idesc_om, accu);
-                if (Cfg::TAIL) umma_bf16_ts(tmem_base + g.o_col + NMAIN, tmem_base + s * 8, dbt, idesc_ot, accu);
-              } else {
-                const uint64_t da = make_sw128_kmajor_desc(smem_u32(sP) + (s >> 2) * (128 * 128) + (s & 3) * 32);
-                umma_bf16<1>(tmem_base + g.o_col, da, dbm, idesc_om, accu);
-                if (Cfg::TAIL) umma_bf16<1>(tmem_base + g.o_col + NMAIN, da, dbt, idesc_ot, accu);
+            const uint64_t vd0 = make_sw128_mnmajor_desc(smem_u32(sV(st)), (uint32_t)(g.BK * 128));
+            const uint64_t vt0 = make_noswz_mnmajor_desc(smem_u32(sVt(st)));
+            const uint64_t pd0 = make_sw128_kmajor_desc(smem_u32(sP));
+            if (leader) {
+              for (int s = 0; s < steps; ++s) {
+                const uint32_t accu = (jb > 0 || s > 0) ? 1u : 0u;
+                const uint64_t dbm = vd0 + (uint64_t)(s * (2048 >> 4));
+                const uint64_t dbt = vt0 + (uint64_t)(s * (512 >> 4));
+                if constexpr (kPTmem) {
+                  umma_bf16_ts(tmem_base + g.o_col, tmem_base + s * 8, dbm, idesc_om, accu);
+                  if (Cfg::TAIL) umma_bf16_ts(tmem_base + g.o_col + NMAIN, tmem_base + s * 8, dbt, idesc_ot, accu);
+                } else {
+                  const uint64_t da = pd0 + (uint64_t)((s >> 2) * ((128 * 128) >> 4) + (s & 3) * 2);
+                  umma_bf16<1>(tmem_base + g.o_col, da, dbm, idesc_om, accu);
+                  if (Cfg::TAIL) umma_bf16<1>(tmem_base + g.o_col + NMAIN, da, dbt, idesc_ot, accu);
+                }
               }
+              if (!g.resident || qt == qt1 - 1) umma_commit<1>(kv_empty(st));   // stage free once its last reader is done
+              umma_commit<1>(o_full);
             }
-            if (!g.resident || qt == qt1 - 1) umma_commit<1>(kv_empty(st));   // stage free once its last reader is done
-            umma_commit<1>(o_full);
+            __syncwarp();
           }
         }
       }

@@ -193,7 +193,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA) =====================
-    if (is_leader && lane == 0) {
+    // The whole warp runs the loop (waits and descriptor arithmetic stay warp-uniform, so the operands sit in uniform
+    // registers and consecutive tcgen05.mma issue back to back); one elected lane issues.  With a single-lane region
+    // the compiler wraps every MMA in a ~20-instruction uniformisation loop, which is longer than a 128 x 192 MMA runs.
+    if (is_leader) {
+      const bool issuer = elect_one();
       constexpr uint32_t idesc = make_idesc_bf16_f32(kBlockM * kCta, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
@@ -207,17 +211,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int64_t kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t a0 = smem_a(stage), b0 = smem_b(stage);
+          const uint64_t da0 = make_sw128_kmajor_desc(smem_a(stage));
+          const uint64_t db0 = make_sw128_kmajor_desc(smem_b(stage));
+          const uint32_t acc0 = kb > 0 ? 1u : 0u;
+          if (issuer) {
+            umma_bf16<kCta>(d_tmem, da0, db0, idesc, acc0);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t da = make_sw128_kmajor_desc(a0 + k * 32);
-            const uint64_t db = make_sw128_kmajor_desc(b0 + k * 32);
-            umma_bf16<kCta>(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 1; k < kBlockK / 16; ++k)   // +32 bytes along K per step = +2 in the descriptor's 16-byte units
+              umma_bf16<kCta>(d_tmem, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, 1u);
+            umma_commit<kCta>(empty_bar(stage));  // smem slot reusable once these MMAs retire
           }
-          umma_commit<kCta>(empty_bar(stage));  // smem slot reusable once these MMAs retire
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit<kCta>(tmem_full_bar(as));   // accumulator complete -> epilogue
+        if (issuer) umma_commit<kCta>(tmem_full_bar(as));   // accumulator complete -> epilogue
+        __syncwarp();
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -461,28 +469,29 @@ int gemm_init() {
   return OSB_OK;
 }
 
-// Tile width: measured on B200 (profiles/r01_gemm_tune_v3.log) the 256-wide tile wins whenever the padding
-// of N to a multiple of 256 wastes <= 12 % (fixed per-tile cost ~ 100 columns' worth of MMA time); otherwise
-// take the candidate minimising (tiles per cluster) x (width + fixed cost).
-static int pick_block_n(int64_t M, int64_t N, int cta) {
+// Tile width: minimise (waves of tiles over the clusters) x (tile width) / (relative efficiency of that width).
+// Wider tiles amortise the per-tile epilogue and re-read A less often; the efficiencies are the measured per-FLOP rates
+// of full waves on the STDiT3 shapes (profiles/r01_gemm_tune_v5.log): e.g. N = 1152 runs 5.19 -> 6 waves of 192 columns
+// (1152 column-times) against 4.32 -> 5 waves of 256 (1280), and 192 wins; N = 4608 divides evenly by 256, which wins.
+static int pick_block_n(int64_t M, int64_t N, int cta, bool has_res) {
   if (N <= 64) return 64;
-  auto waste = [&](int bn) { return (double)((N + bn - 1) / bn * bn) / (double)N; };
-  if (waste(256) <= 1.12) return 256;
-  if (waste(192) <= 1.12) return 192;
   const int cands[3] = {256, 192, 128};
+  // measured per-wave time of a 192-wide tile relative to 0.75 x a 256-wide one: 0.92-0.94 with the residual ring in the
+  // epilogue (it is the epilogue that paces those tiles), 0.86-0.89 without
+  const double eff[3] = {1.0, has_res ? 0.93 : 0.87, 0.78};
   const int64_t tile_m = (int64_t)kBlockM * cta;
   const int64_t clusters = sm_count() / cta;
   int best = 256;
-  int64_t best_cost = INT64_MAX;
-  for (int bn : cands) {
+  double best_cost = 1e300;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
     const int64_t tiles = ((M + tile_m - 1) / tile_m) * ((N + bn - 1) / bn);
-    const int64_t per_cluster = (tiles + clusters - 1) / clusters;
-    const int64_t cost = per_cluster * (bn + 100);
-    if (cost < best_cost) { best_cost = cost; best = bn; }
+    const int64_t waves = (tiles + clusters - 1) / clusters;
+    const double cost = (double)waves * bn / eff[i];
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
   }
   return best;
 }
-
 
 // ------------------------------------------------------------------------------------------
 // causal 3D convolution as implicit GEMM (NDHWC, input already replicate-padded by osb_vae_prep)
@@ -562,9 +571,9 @@ extern "C" int osb_gemm_bf16(const osb_gemm_args* args, void* stream) {
               "osb_gemm_bf16: bias must be 16-byte aligned");
   int cta = a.cta_group ? a.cta_group : 2;
   OSB_REQUIRE(cta == 1 || cta == 2, "osb_gemm_bf16: cta_group must be 0, 1 or 2");
-  int bn = a.block_n ? a.block_n : pick_block_n(a.M, a.N, cta);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool has_res = (a.epilogue == OSB_EPI_BIAS_GATE_RES) && a.R != nullptr;
+  int bn = a.block_n ? a.block_n : pick_block_n(a.M, a.N, cta, has_res);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define OSB_GEMM_CASE(BN, CG)                                                   \
   if (bn == BN && cta == CG)                                                    \
     return has_res ? launch_gemm<BN, CG, true>(a, s) : launch_gemm<BN, CG, false>(a, s);
