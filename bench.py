@@ -234,6 +234,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true", help="replay the step as one CUDA graph (model.capture)")
     ap.add_argument("--no-vae", action="store_true", help="skip the VAE leg (encode/decode fps of BASELINE.json's metric)")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="after warm-up, bracket ONE step with cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`: "
+                         "the launch list of exactly one step; prints no bench line)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "osb200" else args.warmup
 
@@ -302,6 +305,13 @@ def main():
 
     for _ in range(args.warmup):
         step_resident()
+    if args.profile_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
