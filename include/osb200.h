@@ -108,7 +108,8 @@ typedef struct osb_attn_short_args {
   const void* q_norm_w2;          /* optional second RMSNorm weight pair used by tokens >= norm_split: the     */
   const void* k_norm_w2;          /*   joint txt|img sequence of MMDiT has per-stream QKNorm (layers.py:222,238) */
   int32_t norm_split;
-  int32_t reserved;               /* implementation switch: 0 auto, 1 resident-key kernel, 2 flash (P via smem), 3 flash (P in TMEM) */
+  int32_t reserved;               /* implementation switch: 0 auto, 1 resident-key kernel, 2 flash (P via smem), 3 flash (P in TMEM),
+                                     4 two-slot ping-pong kernel (resident key sets <= 320 keys, head_dim <= 72; other shapes fall back to auto) */
   int32_t rope_half;              /* 1: rope tables are applied with the rotate-half pairing (i, i + D/2) of HF /   */
   int32_t reserved2;              /*    Liger RoPE (math.py:27); 0: interleaved pairs (2i, 2i+1) (math.py:60-65)     */
 } osb_attn_short_args;

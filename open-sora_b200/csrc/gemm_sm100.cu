@@ -279,6 +279,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {
+        // bias / gate of this lane's 8 columns: the same for the 4 row groups below, fetched once per chunk and before the
+        // TMEM load so their L1 latency is off the per-row path (the gate row only changes at a modulation-group boundary)
+        const int64_t nl = n_blk * BLOCK_N + c0 + half * 32 + (lane & 3) * 8;
+        const bool nl_ok = nl < p.N;
+        uint4 bias_u = make_uint4(0, 0, 0, 0);
+        if (p.bias && nl_ok) bias_u = __ldg(reinterpret_cast<const uint4*>(p.bias + nl));
+        float4 gate0 = make_float4(1.f, 1.f, 1.f, 1.f), gate1 = gate0;
+        bool gate_uniform = false;
+        if (!kConv && p.epilogue == OSB_EPI_BIAS_GATE_RES && p.gate != nullptr && nl_ok) {
+          const uint32_t g_first = (uint32_t)row0 / group_rows32, g_last = (uint32_t)(row0 + 31) / group_rows32;
+          if (g_first == g_last) {
+            gate_uniform = true;
+            int64_t gi = g_first;
+            if (p.mod_index) gi = p.mod_index[gi];
+            const float* gate_row = p.gate + gi * p.gate_stride + nl;
+            gate0 = __ldg(reinterpret_cast<const float4*>(gate_row));
+            gate1 = __ldg(reinterpret_cast<const float4*>(gate_row + 4));
+          }
+        }
         uint32_t v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + c0 + half * 32);
         tmem_ld_32x32b_x32(taddr, v);
@@ -325,8 +344,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const float4 a1 = *reinterpret_cast<const float4*>(stage_w + rr * kStagePitch + g4 * 8 + 4);
             float acc[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             if (p.bias) {
-              const uint4 bu = __ldg(reinterpret_cast<const uint4*>(p.bias + n));
-              const uint32_t bw[4] = {bu.x, bu.y, bu.z, bu.w};
+              const uint32_t bw[4] = {bias_u.x, bias_u.y, bias_u.z, bias_u.w};
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const float2 f = unpack_bf16x2(bw[k]);
@@ -339,11 +357,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               for (int k = 0; k < 8; ++k) acc[k] = gelu_tanh(acc[k]);
             } else if (p.epilogue == OSB_EPI_BIAS_GATE_RES) {
               if (p.gate != nullptr) {
-                int64_t gi = (uint32_t)row / group_rows32;
-                if (p.mod_index) gi = p.mod_index[gi];
-                const float* gate_row = p.gate + gi * p.gate_stride + n;
-                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate_row));
-                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate_row + 4));
+                float4 g0 = gate0, g1 = gate1;
+                if (!gate_uniform) {   // this warp's 32 rows straddle two modulation groups (or conv row order)
+                  int64_t gi = (uint32_t)row / group_rows32;
+                  if (p.mod_index) gi = p.mod_index[gi];
+                  const float* gate_row = p.gate + gi * p.gate_stride + n;
+                  g0 = __ldg(reinterpret_cast<const float4*>(gate_row));
+                  g1 = __ldg(reinterpret_cast<const float4*>(gate_row + 4));
+                }
                 acc[0] *= g0.x; acc[1] *= g0.y; acc[2] *= g0.z; acc[3] *= g0.w;
                 acc[4] *= g1.x; acc[5] *= g1.y; acc[6] *= g1.z; acc[7] *= g1.w;
               }

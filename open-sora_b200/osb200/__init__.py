@@ -297,7 +297,7 @@ def attn_short(q, k, v, out, *, num_seqs: int, seqs_per_batch: int, q_strides, k
     a.k_norm_w2 = k_norm_w2.data_ptr() if k_norm_w2 is not None else None
     a.norm_split = norm_split
     a.rope_half = int(rope_half)
-    a.reserved = impl if impl else ATTN_IMPL  # 0 = library default; 1 resident keys, 2 flash (P via smem), 3 flash (P in TMEM)
+    a.reserved = impl if impl else ATTN_IMPL  # 0 = library default; 1 resident keys, 2 flash (P via smem), 3 flash (P in TMEM), 4 ping-pong
     with _Timed("attn_short", 4.0 * num_seqs * Lq * Lk * num_heads * head_dim):  # QK^T + PV FLOPs
         _check(_lib.osb_attn_short(C.byref(a), _stream()), "osb_attn_short")
     return out
