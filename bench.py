@@ -29,6 +29,8 @@ sys.path.insert(0, os.path.join(ROOT, "open-sora_b200"))
 import torch  # noqa: E402
 
 METRIC = "denoise-steps/sec STDiT3-XL/2 64x32x32 bf16"
+WORKLOAD = ("STDiT3-XL/2 (depth 28x2, C=1152, 16x72 heads) one denoise forward, latent 1x4x64x32x32 "
+            "(T=64,S=256), text 300x4096 (260 valid)")
 UNIT = "steps/s"
 T_LAT, H_LAT, W_LAT = 64, 32, 32
 FLOP_PER_STEP = 36.13e12  # BASELINE.md §3 / SURVEY.md §8d, per sample per forward
@@ -137,10 +139,11 @@ def run_reference(args, rank):
     v = sum(vals) / len(vals)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True,
+        "scaling": "weak" if args.parallel == "dp" else "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "STDiT3-XL/2 one denoise forward, latent 1x4x64x32x32, text 300x4096 (CPU oracle port; "
-                               "STDiT3 is absent from the reference checkout, SURVEY.md §0)"},
+        "config": {"workload": WORKLOAD, "implementation": "CPU oracle port of the path (STDiT3 is absent from the reference "
+                                                           "checkout, SURVEY.md §0), all host threads"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -368,10 +371,9 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if mode == "dp" else "strong",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if args.parallel == "dp" else "strong",   # the --parallel mode the N > 1 runs of this line use
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic (seeded N(0,1) latents / T5 embeddings, random-init weights)",
-        "config": {"workload": "STDiT3-XL/2 (depth 28x2, C=1152, 16x72 heads) one denoise forward, latent 1x4x64x32x32 "
-                               "(T=64,S=256), text 300x4096 (260 valid)", "parallelism": mode + str(world), "cuda_graph": bool(args.graph),
+        "config": {"workload": WORKLOAD, "parallelism": mode + str(world), "cuda_graph": bool(args.graph),
                    "l2": "weights 2.2 GB + activations stream through every step (>> 126 MB L2): inputs larger than L2",
                    "algorithmic_tflop_per_step": FLOP_PER_STEP / 1e12},
         "clocks": clk, "gpu_launches": launches,
