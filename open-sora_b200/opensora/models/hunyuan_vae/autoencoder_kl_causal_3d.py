@@ -103,8 +103,7 @@ class AutoencoderKLCausal3D(nn.Module):
         import osb200
 
         w = self.quant_conv.weight
-        if not w.is_cuda or w.dtype != torch.bfloat16:
-            raise osb200.OsbError("AutoencoderKLCausal3D (osb200) runs on CUDA in bfloat16 only; no CPU / eager fallback")
+        osb200.require_cuda_bf16(w, "AutoencoderKLCausal3D")
         return osb200
 
     @staticmethod

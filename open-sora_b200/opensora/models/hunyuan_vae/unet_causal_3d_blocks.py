@@ -61,8 +61,7 @@ class CausalConv3d(nn.Module):
 
     def forward(self, x, norm: nn.GroupNorm | None = None, silu: bool = False, up=(1, 1, 1), residual=None):
         osb = _osb()
-        if not x.is_cuda or x.dtype != torch.bfloat16:
-            raise osb.OsbError("hunyuan_vae (osb200) runs on CUDA in bfloat16, channels-last inside; no fallback")
+        osb.require_cuda_bf16(x, "hunyuan_vae CausalConv3d (channels-last inside)")
         wp, bp, narrow, cp, cout = self._weights()
         if x.shape[-1] % 8:  # e.g. a 4-channel latent: zero-pad channels once (weights are zero there too)
             x = torch.nn.functional.pad(x, (0, -x.shape[-1] % 8))

@@ -157,8 +157,7 @@ class Modulation(nn.Module):
 
 def _check(x: Tensor):
     osb = _osb()
-    if not x.is_cuda or x.dtype != torch.bfloat16:
-        raise osb.OsbError("MMDiT (osb200) runs on CUDA in bfloat16 only; there is no CPU / eager fallback")
+    osb.require_cuda_bf16(x, "MMDiT")
     return osb
 
 

@@ -289,9 +289,7 @@ class STDiT3(nn.Module):
         import osb200 as osb
 
         w0 = self.x_embedder.proj.weight
-        if not w0.is_cuda or w0.dtype != torch.bfloat16:
-            raise osb.OsbError("STDiT3 (osb200) runs on CUDA in bfloat16 only: call .cuda().to(torch.bfloat16); "
-                               "there is no CPU / eager fallback")
+        osb.require_cuda_bf16(w0, "STDiT3")
         dev = w0.device
         bf = torch.bfloat16
         C, Hh, D = self.hidden_size, self.num_heads, self.head_dim

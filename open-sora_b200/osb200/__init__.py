@@ -217,6 +217,16 @@ def _need(t, dtype, name):
     init(t.device.index)
 
 
+def require_cuda_bf16(t, what: str) -> None:
+    """The product path has no CPU / eager fallback: the host-side models call this on entry so that a model left on the
+    CPU or in another dtype fails loudly instead of silently running somewhere else."""
+    import torch
+
+    if not t.is_cuda or t.dtype != torch.bfloat16:
+        raise OsbError(f"{what} (osb200) runs on CUDA in bfloat16 only: call .cuda().to(torch.bfloat16); "
+                       "there is no CPU / eager fallback")
+
+
 def ln_modulate(x, shift, scale, *, group_rows: int, mod_index=None, eps: float = 1e-6, out=None):
     """y = LN(x) * (1 + scale[g]) + shift[g];  x bf16 [rows, C]; shift/scale fp32 [G, C] views."""
     import torch

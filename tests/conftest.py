@@ -11,3 +11,18 @@ for p in (ROOT, PKG):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200, sm_100a); run with -m gpu")
+
+
+import pytest
+
+
+@pytest.fixture
+def fake_osb(monkeypatch):
+    """Install the CPU stand-in of the binding (tests/fake_osb200.py) as `osb200` for one test: the host-side models
+    import the binding lazily at call time, so their shape / stride / caching logic runs on the CPU against the
+    documented contract of every entry point.  The real module is restored afterwards."""
+    from tests import fake_osb200
+
+    fake_osb200.reset()
+    monkeypatch.setitem(sys.modules, "osb200", fake_osb200)
+    return fake_osb200

@@ -103,3 +103,19 @@ def test_model_forward_has_no_cpu_fallback():
     with pytest.raises(osb200.OsbError):
         m(torch.zeros(1, 4, 2, 4, 4), torch.zeros(1), torch.zeros(1, 1, 300, 4096), fps=torch.ones(1),
           height=torch.ones(1), width=torch.ones(1))
+
+
+def test_product_tree_knows_nothing_of_the_test_double_or_the_oracle():
+    """tests/fake_osb200.py (host-logic stand-in) and oracle/ are test infrastructure: no file of the shipped package may
+    reference either, so there is no path by which the product could route around the CUDA library."""
+    import os
+
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "open-sora_b200")
+    offenders = []
+    for d, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(d, f), errors="ignore").read()
+                if "fake_osb200" in txt or "import oracle" in txt or "from oracle" in txt:
+                    offenders.append(os.path.join(d, f))
+    assert not offenders, offenders

@@ -1,0 +1,77 @@
+"""Host-side logic of the MMDiT drop-in (`opensora/models/mmdit/{layers,model}.py`: processors, both QKV layouts, both RoPE
+layouts, modulation plumbing, the conditioning residual) on the CPU, through the stand-in of the binding, against the
+oracle that tests/test_oracle_cpu.py pins to the executed reference source."""
+import pytest
+import torch
+
+from tests.test_mmdit_gpu import CFG, _ids
+from tests.util import rel_l2
+
+
+def _rand_model(fused, liger=False):
+    from opensora.registry import MODELS, build_module
+
+    torch.manual_seed(7)
+    m = build_module(dict(type="flux", fused_qkv=fused, use_liger_rope=liger, **CFG), MODELS, device_map="cpu",
+                     torch_dtype=torch.float32)
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.endswith("scale"):
+                p.copy_(1 + 0.2 * torch.randn(p.shape, generator=g))
+            elif p.dim() == 1 or "cond_in" in n:
+                p.copy_(0.05 * torch.randn(p.shape, generator=g))
+    return m.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("fused,liger", [(True, False), (False, False), (False, True)])
+def test_mmdit_model_host_logic(fake_osb, fused, liger):
+    from oracle import mmdit_oracle as M
+
+    m = _rand_model(fused, liger)
+    B, Lt, (T, H, W) = 2, 24, (2, 4, 6)
+    g = torch.Generator().manual_seed(3)
+    rb = lambda *s: torch.randn(*s, generator=g).to(torch.bfloat16)  # noqa: E731
+    txt_ids, img_ids = _ids(B, Lt, T, H, W)
+    inp = dict(img=rb(B, T * H * W, 64), img_ids=img_ids, txt=rb(B, Lt, 128), txt_ids=txt_ids,
+               timesteps=torch.tensor([0.3, 0.8]), y_vec=rb(B, 96), cond=rb(B, T * H * W, 68), guidance=torch.tensor([4.0, 7.5]))
+    with torch.no_grad():
+        out = m(**inp)
+    cfg = dict(CFG, fused_qkv=fused, use_liger_rope=liger)
+    W32 = {k: v.float() for k, v in m.state_dict().items()}
+    finp = {k: (v.float() if v.is_floating_point() else v) for k, v in inp.items()}
+    ref = M.model_forward(W32, cfg, finp["img"], finp["img_ids"], finp["txt"], finp["txt_ids"], finp["timesteps"],
+                          finp["y_vec"], cond=finp["cond"], guidance=finp["guidance"])
+    Wb = dict(m.state_dict())
+    noise = M.model_forward(Wb, cfg, inp["img"], inp["img_ids"], inp["txt"], inp["txt_ids"], inp["timesteps"].to(torch.bfloat16),
+                            inp["y_vec"], cond=inp["cond"], guidance=inp["guidance"].to(torch.bfloat16))
+    r, rn = rel_l2(out, ref), rel_l2(noise, ref)
+    assert out.shape == ref.shape
+    assert r < 2e-2 and r < max(1.5 * rn, 5e-3), (r, rn)
+    # one attention call per block over the joint txt|img sequence, with the second norm-weight pair for the img part
+    attn = [c for c in fake_osb.calls if c[0] == "attn_short"]
+    assert len(attn) == CFG["depth"] + CFG["depth_single_blocks"]
+    assert all(c[1][1] == Lt + T * H * W for c in attn)
+
+
+def test_processor_hook_is_the_plugin_point(fake_osb):
+    from opensora.models.mmdit.layers import DoubleStreamBlockProcessor
+
+    m = _rand_model(True)
+    seen = []
+
+    class Spy(DoubleStreamBlockProcessor):
+        def __call__(self, attn, img, txt, vec, pe):
+            seen.append(tuple(img.shape))
+            return super().__call__(attn, img, txt, vec, pe)
+
+    for b in m.double_blocks:
+        assert isinstance(b.get_processor(), DoubleStreamBlockProcessor)
+        b.set_processor(Spy())
+    txt_ids, img_ids = _ids(1, 8, 1, 4, 4)
+    bf = torch.bfloat16
+    with torch.no_grad():
+        out = m(img=torch.randn(1, 16, 64).to(bf), img_ids=img_ids, txt=torch.randn(1, 8, 128).to(bf), txt_ids=txt_ids,
+                timesteps=torch.tensor([0.5]), y_vec=torch.randn(1, 96).to(bf), cond=torch.randn(1, 16, 68).to(bf),
+                guidance=torch.tensor([4.0]))
+    assert len(seen) == CFG["depth"] and out.shape == (1, 16, 64) and torch.isfinite(out.float()).all()

@@ -1,0 +1,94 @@
+"""Host-side logic of the causal-VAE drop-in (`opensora/models/hunyuan_vae/*`: NDHWC plumbing, weight packing incl. the
+narrow first / last layers, causal padding, first-frame up-sampling, down-sampling strides, mid-block attention, the
+tiled / blended modes) on the CPU through the stand-in of the binding, against the goldens produced by EXECUTING the
+reference classes (tests/golden/vae_blocks.npz, vae_tiled.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import rel_l2
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _golden(name):
+    return {k: torch.from_numpy(v) for k, v in np.load(os.path.join(HERE, "golden", name)).items()}
+
+
+def _model(G, **kw):
+    from opensora.registry import MODELS, build_module
+
+    m = build_module(dict(type="hunyuan_vae", block_out_channels=(16, 32, 32, 32), layers_per_block=1, norm_num_groups=4,
+                          latent_channels=4, **kw), MODELS, device_map="cpu")
+    m.encoder.load_state_dict({k[4:]: v for k, v in G.items() if k.startswith("enc.")})
+    m.decoder.load_state_dict({k[4:]: v for k, v in G.items() if k.startswith("dec.")})
+    return m
+
+
+def test_encoder_decoder_against_reference_goldens(fake_osb):
+    from oracle import vae_oracle as V
+
+    G = _golden("vae_blocks.npz")
+    m = _model(G).to(torch.bfloat16)
+    down, up = V.stage_plan(4, 4, 8)
+    Wb = {k: v.to(torch.bfloat16) for k, v in G.items()}
+    ze_bf = V.encoder({k[4:]: v for k, v in Wb.items() if k.startswith("enc.")}, Wb["enc_x"], groups=4, strides=down)
+    yd_bf = V.decoder({k[4:]: v for k, v in Wb.items() if k.startswith("dec.")}, Wb["enc_y"][:, :4], groups=4, factors=up)
+    fe, fd = rel_l2(ze_bf, G["enc_y"]), rel_l2(yd_bf, G["dec_y"])
+    with torch.no_grad():
+        z = m._to_ncdhw(m.encoder(m._to_ndhwc(G["enc_x"].to(torch.bfloat16), cpad=8)))
+        y = m._to_ncdhw(m.decoder(m._to_ndhwc(G["enc_y"][:, :4].to(torch.bfloat16))))
+    assert z.shape == G["enc_y"].shape and rel_l2(z, G["enc_y"]) < max(1.5 * fe, 1e-2)
+    assert y.shape == G["dec_y"].shape and rel_l2(y, G["dec_y"]) < max(1.5 * fd, 1e-2)
+    convs = [c for c in fake_osb.calls if c[0] == "conv3d"]
+    assert any(c[1][3] for c in convs), "the 3-channel input layer uses the narrow (kw x channels folded) packing"
+    assert {c[1][2] for c in convs} >= {(1, 1, 1), (1, 2, 2), (2, 2, 2)}, "down-samplers run as strided convolutions"
+
+
+@pytest.mark.parametrize("tag,sp,tp", [("none", False, False), ("spatial", True, False), ("temporal", False, True), ("both", True, True)])
+def test_tiled_modes_against_reference_goldens(fake_osb, tag, sp, tp):
+    from oracle import vae_oracle as V
+
+    G, GT = _golden("vae_blocks.npz"), _golden("vae_tiled.npz")
+    m = _model(G, sample_size=32, sample_tsize=8, use_spatial_tiling=sp, use_temporal_tiling=tp)
+    with torch.no_grad():
+        m.quant_conv.weight.copy_(GT["quant_w"]); m.quant_conv.bias.copy_(GT["quant_b"])
+        m.post_quant_conv.weight.copy_(GT["post_w"]); m.post_quant_conv.bias.copy_(GT["post_b"])
+    m = m.to(torch.bfloat16)
+    with torch.no_grad():
+        z = m.encode(GT["x"], sample_posterior=False)
+        y = m.decode(GT[f"z_{tag}"])
+    down, up = V.stage_plan(4, 4, 8)
+    bf = lambda d, pfx: {k[len(pfx):]: v.to(torch.bfloat16) for k, v in d.items() if k.startswith(pfx)}  # noqa: E731
+    We, Wd = bf(G, "enc."), bf(G, "dec.")
+    qw, qb, pw, pb = (GT[k].to(torch.bfloat16) for k in ("quant_w", "quant_b", "post_w", "post_b"))
+    encode, decode = V.tiled_autoencoder(lambda x: V.causal_conv3d(V.encoder(We, x, groups=4, strides=down), qw, qb),
+                                         lambda t: V.decoder(Wd, V.causal_conv3d(t, pw, pb), groups=4, factors=up),
+                                         sample_size=32, sample_tsize=8, spatial=sp, temporal=tp)
+    zf = rel_l2(0.476986 * encode(GT["x"].to(torch.bfloat16))[:, :4], GT[f"z_{tag}"])
+    yf = rel_l2(decode((GT[f"z_{tag}"] / 0.476986).to(torch.bfloat16)), GT[f"y_{tag}"])
+    assert z.shape == GT[f"z_{tag}"].shape and y.shape == GT[f"y_{tag}"].shape
+    assert rel_l2(z, GT[f"z_{tag}"]) < max(1.5 * zf, 1e-2) and rel_l2(y, GT[f"y_{tag}"]) < max(1.5 * yf, 1e-2)
+
+
+def test_causal_conv_is_causal_and_latent_size_api(fake_osb):
+    from opensora.models.hunyuan_vae.unet_causal_3d_blocks import CausalConv3d
+    from opensora.registry import MODELS, build_module
+
+    torch.manual_seed(0)
+    c = CausalConv3d(64, 64, 3).to(torch.bfloat16)
+    x = torch.randn(1, 5, 6, 7, 64).to(torch.bfloat16)
+    y0 = c(x)
+    x2 = x.clone()
+    x2[:, -1] += 1.0
+    y1 = c(x2)
+    assert torch.equal(y0[:, :-1], y1[:, :-1]) and not torch.equal(y0[:, -1], y1[:, -1])
+    m = build_module(dict(type="hunyuan_vae", block_out_channels=(16, 32, 32, 32), layers_per_block=1, norm_num_groups=4,
+                          latent_channels=4), MODELS, device_map="cpu").to(torch.bfloat16)
+    v = torch.rand(1, 3, 9, 32, 32) * 2 - 1
+    with torch.no_grad():
+        z = m.encode(v, sample_posterior=False)
+        rec, _, z2 = m(v, sample_posterior=False)
+    assert list(z.shape) == [1, 4] + m.get_latent_size([9, 32, 32]) and rec.shape == v.shape and torch.equal(z, z2)
