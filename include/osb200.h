@@ -41,6 +41,8 @@ int osb_version(void);
 const char* osb_last_error(void);
 /* number of kernels this library has launched since process start (bench.py's gpu_launches) */
 int64_t osb_launch_count(void);
+/* hits / misses of the per-process TMA descriptor cache (descriptors are keyed by pointer, shape, stride and box) */
+void osb_tmap_cache_stats(int64_t* hits, int64_t* misses);
 
 /* ---- LayerNorm (no affine) + adaLN modulate ---------------------------------------------- */
 /* y[r,:] = LN(x[r,:]) * (1 + scale[g,:]) + shift[g,:],  g = mod_index ? mod_index[r / group_rows]
@@ -119,6 +121,70 @@ typedef struct osb_attn_short_args {
  * (`attention`), layers.py:126-135 (QKNorm), and upstream STDiT3 Attention / MultiHeadCrossAttention
  * (SURVEY.md §8a-S, Appendix A). */
 int osb_attn_short(const osb_attn_short_args* args, void* stream);
+
+/* ---- head tiles: projection GEMM -> attention without a layout pass ------------------------------------ */
+/* A head tile is the HBM image of one tcgen05 operand tile: tile_rows <= 128 token rows of ONE head, head_dim
+ * padded to a multiple of 16, 64-column chunks in the 128-byte-swizzle layout followed by the head-dim tail in the
+ * no-swizzle core-matrix layout (open-sora_b200/csrc/tiles.cuh).  The projection GEMM writes q / k / v straight into
+ * this form (bias + per-head RMSNorm + RoPE fused in its epilogue) and the attention kernel loads whole tiles with
+ * one bulk copy each.  osb_tile_map says which token row lands in which (tile, row):
+ *   mode 0: sequences are contiguous row blocks        seq = row / L, pos = row % L
+ *   mode 1: frame-major stream viewed along T          row = (b*T + t)*S + s -> seq = b*S + s, pos = t  (L == T)
+ *   G > 1 : G short sequences packed per tile          tile = seq / G, r = (seq % G)*L + pos   (G*L <= tile_rows, tps == 1)
+ *   G == 1: tile = seq*tps + pos / tile_rows, r = pos % tile_rows, tps = ceil(L / tile_rows)                      */
+typedef struct osb_tile_map {
+  int32_t mode, L, S, T, G, tps, tile_rows, reserved;
+} osb_tile_map;
+
+typedef struct osb_head_tiles_args {
+  void* tiles;              /* tile buffer; tile (kidx, head, t) at tiles + kidx*kind_stride + head*head_stride +
+                               t*tile_rows*2*pad16(head_dim), kidx = output column / (num_heads*head_dim)           */
+  int64_t kind_stride;      /* bytes between consecutive num_heads*head_dim wide column groups (q | k | v, or the
+                               k | v pairs of several blocks)                                                        */
+  int64_t head_stride;      /* bytes between heads = tiles per head * tile bytes                                     */
+  osb_tile_map map;
+  int32_t num_heads, head_dim;
+  int32_t nkinds;           /* column group kidx is of kind kidx % nkinds                                            */
+  uint32_t norm_mask;       /* bit k: kind k gets per-head RMSNorm with norm_w[k]        (layers.py:102-135)         */
+  uint32_t rope_mask;       /* bit k: kind k gets interleaved-pair RoPE by position      (math.py:60-65)             */
+  int32_t reserved;
+  const void* norm_w[4];    /* bf16 [head_dim] per kind or NULL                                                      */
+  float norm_eps;
+  int32_t reserved2;
+  const float* rope_cos;    /* fp32 [L, head_dim/2]                                                                  */
+  const float* rope_sin;
+} osb_head_tiles_args;
+
+/* tiles = head_tiles(epilogue(A W^T + bias)): the GEMM of osb_gemm_bf16 (gemm->D / ldd / epilogue / R / gate are
+ * ignored) whose epilogue splits every output row into heads, applies RMSNorm / RoPE in fp32 on the fp32
+ * accumulator and stores each head row once, as bf16, at its place in the tile buffer.
+ * Replaces layers.py:209-214 (qkv Linear), :116-135 (QKNorm) and math.py:27,60-65 (RoPE) - the q/k/v tensors in
+ * token layout never exist.  Requires N % (num_heads*head_dim) == 0, head_dim in {64, 72, 128}. */
+int osb_gemm_head_tiles(const osb_gemm_args* gemm, const osb_head_tiles_args* tiles, void* stream);
+
+/* tiles per head for `rows` token rows under `map` (rows / L sequences) */
+int64_t osb_head_tiles_per_head(const osb_tile_map* map, int64_t rows);
+
+typedef struct osb_attn_tiles_args {
+  const void* q_tiles; const void* k_tiles; const void* v_tiles;  /* tile 0 of head 0 of each operand                */
+  int64_t q_head_stride, kv_head_stride;                          /* bytes between heads                            */
+  osb_tile_map q_map;        /* rows of `out` <-> q tiles; key set i belongs to sequence i (G == 1) or tile i (G > 1) */
+  int32_t kv_tile_rows;      /* rows per key / value tile (multiple of 16, <= 128)                                  */
+  int32_t kv_tiles_per_set;  /* key tiles per sequence: ceil(Lk / kv_tile_rows) (1 for packed sequences)            */
+  int32_t Lk;                /* keys per sequence                                                                   */
+  int32_t num_heads, head_dim;
+  int32_t reserved;
+  int64_t num_seqs;
+  const int32_t* kv_lens;    /* optional [num_seqs]: valid keys per sequence (G == 1)                               */
+  void* out;                 /* bf16, row of token = inverse of q_map, head h at columns [h*head_dim, (h+1)*head_dim) */
+  int64_t out_ld;
+  float softmax_scale;
+  int32_t reserved2;
+} osb_attn_tiles_args;
+
+/* out = softmax(q k^T * scale) v per (sequence, head) over head tiles: persistent CTAs, bulk-copy loads, two
+ * query tiles in flight per CTA (open-sora_b200/csrc/attn_tiles_sm100.cu).  Replaces mmdit/math.py:22-36. */
+int osb_attn_tiles(const osb_attn_tiles_args* args, void* stream);
 
 /* ---- causal 3D VAE: implicit-GEMM convolution + its HBM-bound helpers ----------------------------- */
 typedef struct osb_conv3d_args {

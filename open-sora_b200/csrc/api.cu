@@ -6,6 +6,8 @@
 #include <stdlib.h>
 
 #include <atomic>
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -31,12 +33,45 @@ bool pdl_enabled() {
 }
 int sm_count() { return g_sms; }
 
+// Descriptor cache ("process-global state limited to per-device immutable caches (TMA descriptors keyed
+// by pointer/shape)").  A tensor map is a pure function of (base, rows, cols, ld, box), so an entry can never go stale;
+// the block loop of a denoise step re-uses ~40 distinct operand views 346 times, and a CUDA-graph capture or a
+// sequence-parallel rank with 2 048 tokens is host-bound on cuTensorMapEncodeTiled otherwise.
+struct TmapKey {
+  uint64_t base, rows, cols, ld, box;
+  bool operator==(const TmapKey& o) const { return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box == o.box; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = k.base * 0x9E3779B97F4A7C15ull;
+    h ^= (k.rows + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.cols + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.ld + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.box + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    return (size_t)h;
+  }
+};
+static std::mutex g_tmap_mu;
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+static std::atomic<int64_t> g_tmap_hits{0}, g_tmap_misses{0};
+
 int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
   if (!g_encode) {
     set_error("osb_init() has not been called");
     return OSB_ERR_NOT_INIT;
   }
+  const TmapKey key{reinterpret_cast<uint64_t>(base), rows, cols, ld, ((uint64_t)box_rows << 32) | box_cols};
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *map = it->second;
+      g_tmap_hits.fetch_add(1, std::memory_order_relaxed);
+      return OSB_OK;
+    }
+  }
+  g_tmap_misses.fetch_add(1, std::memory_order_relaxed);
   if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 2) & 15)) {
     set_error("TMA operand must be 16-byte aligned (base %p, ld %llu elements)", base,
               (unsigned long long)ld);
@@ -55,6 +90,11 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_
               (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld,
               box_rows, box_cols);
     return OSB_ERR_CUDA;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (g_tmap_cache.size() >= 8192) g_tmap_cache.clear();   // bounded: a long-lived process with many shapes starts over
+    g_tmap_cache.emplace(key, *map);
   }
   return OSB_OK;
 }
@@ -93,6 +133,7 @@ int make_tmap_5d_bf16(CUtensorMap* map, const void* base, const uint64_t dims[5]
 
 int gemm_init();   // gemm_sm100.cu
 int attn_init();   // attn_short_sm100.cu
+int attn_tiles_init();   // attn_tiles_sm100.cu
 
 }  // namespace osb
 
@@ -102,8 +143,18 @@ int osb_version(void) { return 100; }
 const char* osb_last_error(void) { return osb::g_err; }
 int64_t osb_launch_count(void) { return osb::g_launches.load(); }
 
+void osb_tmap_cache_stats(int64_t* hits, int64_t* misses) {
+  if (hits) *hits = osb::g_tmap_hits.load();
+  if (misses) *misses = osb::g_tmap_misses.load();
+}
+
 int osb_init(int device) {
   using namespace osb;
+  // bind for the duration of the call only: the caller's current device is restored (kernels launch on the device
+  // that owns the stream they are given)
+  int prev_device = -1;
+  OSB_CHECK_CUDA(cudaGetDevice(&prev_device));
+  struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_device == device ? -1 : prev_device};
   OSB_CHECK_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
   OSB_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -125,6 +176,8 @@ int osb_init(int device) {
   int rc = gemm_init();
   if (rc) return rc;
   rc = attn_init();
+  if (rc) return rc;
+  rc = attn_tiles_init();
   if (rc) return rc;
   g_init = true;
   return OSB_OK;

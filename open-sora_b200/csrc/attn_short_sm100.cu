@@ -19,6 +19,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tiles.cuh"
 
 namespace osb {
 
@@ -61,24 +62,6 @@ struct AttnCfg {
   static_assert(TAIL == 0 || TAIL == 16, "head_dim tail must be one MMA K step");
   static_assert(D % 8 == 0, "head_dim must be a multiple of 8");
 };
-
-// byte offset of 16-byte unit `u` (0..7) of row `r` inside a [rows x 64] bf16 SW128 K-major chunk
-__device__ __forceinline__ uint32_t sw128_off(int r, int u) {
-  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((u ^ (r & 7)) << 4));
-}
-// byte offset of unit `u` (0..1) of row `r` inside a [rows x 16] bf16 no-swizzle K-major tile:
-// core matrices of 8 rows x 16 B; K-adjacent core matrices 128 B apart (LBO), 8-row groups 256 B (SBO)
-__device__ __forceinline__ uint32_t tail_off(int r, int u) {
-  return (uint32_t)((r >> 3) * 256 + u * 128 + (r & 7) * 16);
-}
-__device__ __forceinline__ uint64_t make_noswz_kmajor_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>(128 >> 4) << 16;  // LBO: next core matrix along K
-  d |= static_cast<uint64_t>(256 >> 4) << 32;  // SBO: next 8-row group
-  d |= static_cast<uint64_t>(1) << 46;         // descriptor version (sm_100)
-  return d;                                    // layout type 0 = SWIZZLE_NONE
-}
 
 __device__ __forceinline__ void unpack8(const uint4& t, float* x) {
   const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
@@ -556,28 +539,6 @@ struct FlashGeom {
   int64_t units;             // work units per head
   int64_t items;             // units * heads
 };
-
-__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;  // LBO: next 64-wide block along N
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;                  // SBO: next group of 8 K-rows
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;                          // SWIZZLE_128B
-  return d;
-}
-__device__ __forceinline__ uint64_t make_noswz_mnmajor_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>(256 >> 4) << 16;  // LBO: next group of 8 K-rows
-  d |= static_cast<uint64_t>(128 >> 4) << 32;  // SBO: next 8-wide unit along N
-  d |= static_cast<uint64_t>(1) << 46;
-  return d;
-}
-// kind::f16 instruction descriptor with an MN-major B operand (bit 16)
-__host__ __device__ constexpr uint32_t make_idesc_bf16_f32_bmn(uint32_t M, uint32_t N) {
-  return make_idesc_bf16_f32(M, N) | (1u << 16);
-}
 
 template <int D, bool kPTmem>
 __global__ void __launch_bounds__(kFlashThreads, (D <= 72) ? 2 : 1) attn_flash_kernel(const AttnParams p, const FlashGeom g) {

@@ -11,6 +11,7 @@
 // (opensora/models/mmdit/layers.py:209-214,247-252,277-281,314-334,401) and the fused epilogues
 // replace the separate bias / GELU(tanh) / gate*x+residual elementwise kernels.
 #include "common.cuh"
+#include "tiles.cuh"
 
 namespace osb {
 
@@ -37,6 +38,23 @@ struct GemmEpilogueParams {
   int32_t epilogue;
 };
 
+// Head-tile epilogue (kHT): every output row is split into heads of D = BLOCK_N / 2 columns; per head: bias, optional
+// RMSNorm (fp32 statistics over the fp32 accumulator), optional interleaved-pair RoPE by token position, one rounding
+// to bf16, stored at the row's place inside the head's operand tile (tiles.cuh) - the projection output never exists
+// in token layout.  Column group kidx = col / C (C = heads * D) selects the kind (q / k / v) = kidx % nkinds.
+struct HeadTileParams {
+  uint8_t* base;
+  int64_t kind_stride, head_stride;
+  TileMap map;
+  int32_t tile_bytes;
+  int32_t heads, nkinds;
+  uint32_t norm_mask, rope_mask;
+  const __nv_bfloat16* norm_w[4];
+  float eps;
+  const float* cos;
+  const float* sin;
+};
+
 // Implicit-GEMM view of a causal 3D convolution over a (replicate-)padded NDHWC activation tensor: one
 // CTA owns a Tt x Ht x Wt box of output positions (128 rows); CTA pairs stack two boxes along H.  The K loop
 // walks (kt, kh, kw) taps x 64-channel chunks; every k-block is ONE 5-D TMA box load at the tap's offset.
@@ -49,7 +67,7 @@ struct ConvGeom {
   int32_t cin_chunks;                    // 64-wide channel chunks per tap
 };
 
-template <int BLOCK_N, int kCta, bool kRes>
+template <int BLOCK_N, int kCta, bool kRes, bool kHT = false>
 struct GemmCfg {
   static constexpr int LOAD_N = BLOCK_N / kCta;
   static constexpr int A_BYTES = kBlockM * kBlockK * 2;
@@ -65,15 +83,17 @@ struct GemmCfg {
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
   static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
   static_assert(B_BYTES % 1024 == 0, "W tile must keep 1024-byte swizzle-atom alignment");
-  static_assert(BLOCK_N % 64 == 0, "epilogue works in 64-column chunks");
+  static_assert(kHT || BLOCK_N % 64 == 0, "epilogue works in 64-column chunks");
+  static_assert(BLOCK_N % 16 == 0 && LOAD_N % 8 == 0, "UMMA N / swizzle-atom granularity");
   static_assert(2 * STAGES + 4 + 2 * 4 + 1 <= kBarBytes / 8, "barrier area");
 };
 
-template <int BLOCK_N, int kCta, bool kRes, bool kConv>
+template <int BLOCK_N, int kCta, bool kRes, bool kConv, bool kHT = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                 const __grid_constant__ CUtensorMap tmap_r, const GemmEpilogueParams p, const ConvGeom cg) {
-  using Cfg = GemmCfg<BLOCK_N, kCta, kRes>;
+                 const __grid_constant__ CUtensorMap tmap_r, const GemmEpilogueParams p, const ConvGeom cg,
+                 const HeadTileParams ht) {
+  using Cfg = GemmCfg<BLOCK_N, kCta, kRes, kHT>;
   constexpr int kStages = Cfg::STAGES;
   constexpr int kResStages = Cfg::RES_STAGES;
 
@@ -254,6 +274,130 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     }
+  } else if constexpr (kHT) {
+    // ===================== epilogue warps: head tiles =====================
+    // thread = accumulator row; warps 0-3 / 4-7 of the epilogue take head 0 / 1 of the tile's two heads.  The whole
+    // head row (D fp32 values) sits in registers, so RMSNorm and RoPE need no exchange between threads.
+    constexpr int D = BLOCK_N / 2;
+    using HT = HeadTileCfg<D>;
+    const int e = warp - kFirstEpiWarp;
+    const int q = warp & 3;
+    const int hh = e >> 2;
+    const int C = ht.heads * D;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int64_t m_blk = tile / num_n_blocks, n_blk = tile % num_n_blocks;
+      const int64_t row = m_blk * tile_m + cta_rank * kBlockM + q * 32 + lane;
+      mbar_wait(tmem_full_bar(as), aphase);
+      tc_fence_after();
+      uint32_t raw[D];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + hh * D);
+#pragma unroll
+      for (int c = 0; c + 32 <= D; c += 32) tmem_ld_32x32b_x32(taddr + c, reinterpret_cast<uint32_t(&)[32]>(raw[c]));
+      if constexpr (D % 32 == 8) tmem_ld_32x32b_x8(taddr + D / 32 * 32, reinterpret_cast<uint32_t(&)[8]>(raw[D / 32 * 32]));
+      if constexpr (D % 32 == 16) tmem_ld_32x32b_x16(taddr + D / 32 * 32, reinterpret_cast<uint32_t(&)[16]>(raw[D / 32 * 32]));
+      tmem_ld_wait();
+      // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kCta == 2) mbar_arrive_cluster(tmem_empty_bar(as), 0);
+        else mbar_arrive(tmem_empty_bar(as));
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+      const int64_t col0 = n_blk * BLOCK_N + hh * D;
+      if (col0 >= p.N || row >= p.M) continue;
+      const int kidx = (int)(col0 / C);
+      const int head = (int)(col0 - (int64_t)kidx * C) / D;
+      const int kind = kidx % ht.nkinds;
+      float x[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) x[i] = __uint_as_float(raw[i]);
+      if (p.bias) {
+#pragma unroll
+        for (int u = 0; u < HT::U; ++u) {
+          const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col0) + u);
+          const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = unpack_bf16x2(bw[k]);
+            x[8 * u + 2 * k] += f.x;
+            x[8 * u + 2 * k + 1] += f.y;
+          }
+        }
+      }
+      // token row -> (sequence position, tile, row in tile)
+      int64_t seq;
+      int pos;
+      if (ht.map.mode == 0) {
+        seq = row / ht.map.L;
+        pos = (int)(row - seq * ht.map.L);
+      } else {
+        const int64_t ts = (int64_t)ht.map.T * ht.map.S;
+        const int64_t b = row / ts;
+        const int64_t rem = row - b * ts;
+        pos = (int)(rem / ht.map.S);
+        seq = b * ht.map.S + (rem - (int64_t)pos * ht.map.S);
+      }
+      int64_t tile_i;
+      int r;
+      if (ht.map.G > 1) {
+        tile_i = seq / ht.map.G;
+        r = (int)(seq - tile_i * ht.map.G) * ht.map.L + pos;
+      } else {
+        const int jt = pos / ht.map.TR;
+        tile_i = seq * ht.map.tps + jt;
+        r = pos - jt * ht.map.TR;
+      }
+      if ((ht.norm_mask >> kind) & 1u) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < D; i += 4) { s0 += x[i] * x[i]; s1 += x[i + 1] * x[i + 1]; s2 += x[i + 2] * x[i + 2]; s3 += x[i + 3] * x[i + 3]; }
+        const float rs = rsqrtf(((s0 + s1) + (s2 + s3)) * (1.0f / D) + ht.eps);
+        const __nv_bfloat16* w = ht.norm_w[kind];
+#pragma unroll
+        for (int u = 0; u < HT::U; ++u) {
+          const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w) + u);
+          const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = unpack_bf16x2(ww[k]);
+            x[8 * u + 2 * k] *= rs * f.x;
+            x[8 * u + 2 * k + 1] *= rs * f.y;
+          }
+        }
+      }
+      if ((ht.rope_mask >> kind) & 1u) {
+        const float4* cr = reinterpret_cast<const float4*>(ht.cos + (int64_t)pos * (D / 2));
+        const float4* sr = reinterpret_cast<const float4*>(ht.sin + (int64_t)pos * (D / 2));
+#pragma unroll
+        for (int u = 0; u < HT::U; ++u) {
+          const float4 c4 = __ldg(cr + u), s4 = __ldg(sr + u);
+          const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float a = x[8 * u + 2 * i], b = x[8 * u + 2 * i + 1];
+            x[8 * u + 2 * i] = a * cc[i] - b * sn[i];
+            x[8 * u + 2 * i + 1] = b * cc[i] + a * sn[i];
+          }
+        }
+      }
+      uint8_t* dst = ht.base + (int64_t)kidx * ht.kind_stride + (int64_t)head * ht.head_stride + tile_i * ht.tile_bytes;
+      const int chunk_bytes = ht.map.TR * 128;
+#pragma unroll
+      for (int u = 0; u < HT::UP; ++u) {
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (u < HT::U) {
+          o.x = pack_bf16x2(x[8 * u], x[8 * u + 1]);
+          o.y = pack_bf16x2(x[8 * u + 2], x[8 * u + 3]);
+          o.z = pack_bf16x2(x[8 * u + 4], x[8 * u + 5]);
+          o.w = pack_bf16x2(x[8 * u + 6], x[8 * u + 7]);
+        }
+        if (u < HT::MAIN * 8) *reinterpret_cast<uint4*>(dst + (u >> 3) * chunk_bytes + sw128_off(r, u & 7)) = o;
+        else *reinterpret_cast<uint4*>(dst + HT::MAIN * chunk_bytes + tail_off(r, u - HT::MAIN * 8)) = o;
+      }
+    }
   } else {
     // ===================== epilogue warps =====================
     // TMEM -> registers (thread = accumulator row) -> per-warp fp32 staging tile in smem -> re-read with
@@ -287,8 +431,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (p.bias && nl_ok) bias_u = __ldg(reinterpret_cast<const uint4*>(p.bias + nl));
         float4 gate0 = make_float4(1.f, 1.f, 1.f, 1.f), gate1 = gate0;
         bool gate_uniform = false;
-        if (!kConv && p.epilogue == OSB_EPI_BIAS_GATE_RES && p.gate != nullptr && nl_ok) {
-          const uint32_t g_first = (uint32_t)row0 / group_rows32, g_last = (uint32_t)(row0 + 31) / group_rows32;
+        if (!kConv && p.epilogue == OSB_EPI_BIAS_GATE_RES && p.gate != nullptr && nl_ok && row0 < p.M) {
+          // rows past M (ragged last tile) carry no data: clamp so the prefetch never indexes past the last group
+          const int64_t row_last = row0 + 31 < p.M ? row0 + 31 : p.M - 1;
+          const uint32_t g_first = (uint32_t)row0 / group_rows32, g_last = (uint32_t)row_last / group_rows32;
           if (g_first == g_last) {
             gate_uniform = true;
             int64_t gi = g_first;
@@ -413,17 +559,38 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-template <int BLOCK_N, int kCta, bool kRes, bool kConv>
+template <int BLOCK_N, int kCta, bool kRes, bool kConv, bool kHT = false>
 static int launch_kernel(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tr, const GemmEpilogueParams& p,
-                         const ConvGeom& cg, int64_t tiles, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, kCta, kRes>;
+                         const ConvGeom& cg, int64_t tiles, cudaStream_t stream, const HeadTileParams& ht = HeadTileParams()) {
+  using Cfg = GemmCfg<BLOCK_N, kCta, kRes, kHT>;
   int64_t clusters = sm_count() / kCta;
   if (tiles < clusters) clusters = tiles;
   cudaLaunchAttribute attr[2];
   cudaLaunchConfig_t cfg = launch_config(dim3((unsigned)(clusters * kCta)), dim3(kNumThreads), Cfg::SMEM_BYTES, stream, attr, kCta);
-  OSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BLOCK_N, kCta, kRes, kConv>, ta, tw, tr, p, cg));
+  OSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BLOCK_N, kCta, kRes, kConv, kHT>, ta, tw, tr, p, cg, ht));
   count_launch();
   return OSB_OK;
+}
+
+// head-tile GEMM: BLOCK_N = 2 heads, CTA pairs
+template <int D>
+static int launch_gemm_ht(const osb_gemm_args& a, const HeadTileParams& ht, cudaStream_t stream) {
+  constexpr int BLOCK_N = 2 * D, kCta = 2;
+  using Cfg = GemmCfg<BLOCK_N, kCta, false, true>;
+  CUtensorMap ta, tw;
+  int rc = make_tmap_2d_bf16(&ta, a.A, a.M, a.K, a.lda, kBlockM, kBlockK);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tw, a.W, a.N, a.K, a.ldw, Cfg::LOAD_N, kBlockK);
+  if (rc) return rc;
+  GemmEpilogueParams p = {};
+  p.bias = static_cast<const __nv_bfloat16*>(a.bias);
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.group_rows = a.M;
+  p.epilogue = OSB_EPI_BIAS;
+  const int64_t tile_m = (int64_t)kBlockM * kCta;
+  const int64_t tiles = ((a.M + tile_m - 1) / tile_m) * ((a.N + BLOCK_N - 1) / BLOCK_N);
+  ConvGeom cg = {};
+  return launch_kernel<BLOCK_N, kCta, false, false, true>(ta, tw, ta, p, cg, tiles, stream, ht);
 }
 
 template <int BLOCK_N, int kCta, bool kRes>
@@ -481,8 +648,18 @@ static int init_bn() {
   return OSB_OK;
 }
 
+template <int D>
+static int init_ht() {
+  OSB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<2 * D, 2, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      GemmCfg<2 * D, 2, false, true>::SMEM_BYTES));
+  return OSB_OK;
+}
+
 int gemm_init() {
   int rc = 0;
+  if ((rc = init_ht<64>())) return rc;
+  if ((rc = init_ht<72>())) return rc;
+  if ((rc = init_ht<128>())) return rc;
   if ((rc = init_bn<64>())) return rc;
   if ((rc = init_bn<128>())) return rc;
   if ((rc = init_bn<192>())) return rc;
@@ -660,4 +837,57 @@ extern "C" int osb_conv3d_ndhwc(const osb_conv3d_args* args, void* stream) {
 #undef OSB_CONV_CASE
   set_error("osb_conv3d_ndhwc: unsupported block_n %d", bn);
   return OSB_ERR_UNSUPPORTED;
+}
+
+extern "C" int osb_gemm_head_tiles(const osb_gemm_args* args, const osb_head_tiles_args* targs, void* stream) {
+  using namespace osb;
+  if (!initialised()) { set_error("osb_init() has not been called"); return OSB_ERR_NOT_INIT; }
+  OSB_REQUIRE(args != nullptr && targs != nullptr, "osb_gemm_head_tiles: null args");
+  const osb_gemm_args& a = *args;
+  const osb_head_tiles_args& t = *targs;
+  OSB_REQUIRE(a.A && a.W && t.tiles, "osb_gemm_head_tiles: null operand");
+  OSB_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0 && a.K % 8 == 0, "osb_gemm_head_tiles: bad problem (M %lld N %lld K %lld)",
+              (long long)a.M, (long long)a.N, (long long)a.K);
+  const int D = t.head_dim;
+  OSB_REQUIRE(D == 64 || D == 72 || D == 128, "osb_gemm_head_tiles: head_dim %d not built (64, 72, 128)", D);
+  OSB_REQUIRE(t.num_heads > 0 && t.num_heads % 2 == 0 && a.N % ((int64_t)t.num_heads * D) == 0,
+              "osb_gemm_head_tiles: N (%lld) must be a multiple of num_heads*head_dim with an even head count (%d x %d)",
+              (long long)a.N, t.num_heads, D);
+  OSB_REQUIRE(t.nkinds >= 1 && t.nkinds <= 4, "osb_gemm_head_tiles: nkinds must be 1..4");
+  const osb_tile_map& m = t.map;
+  OSB_REQUIRE(m.mode == 0 || m.mode == 1, "osb_gemm_head_tiles: unknown tile map mode %d", m.mode);
+  OSB_REQUIRE(m.L > 0 && m.G >= 1 && m.tile_rows > 0 && m.tile_rows <= 128 && m.tile_rows % 8 == 0,
+              "osb_gemm_head_tiles: bad tile map (L %d G %d rows %d)", m.L, m.G, m.tile_rows);
+  OSB_REQUIRE(m.G == 1 ? (m.tps == (m.L + m.tile_rows - 1) / m.tile_rows) : (m.G * m.L <= m.tile_rows && m.tps == 1),
+              "osb_gemm_head_tiles: tile map inconsistent (L %d G %d tps %d rows %d)", m.L, m.G, m.tps, m.tile_rows);
+  OSB_REQUIRE(m.mode == 0 ? (a.M % m.L == 0) : (m.S > 0 && m.T == m.L && a.M % ((int64_t)m.S * m.T) == 0),
+              "osb_gemm_head_tiles: M (%lld) is not a whole number of sequences", (long long)a.M);
+  OSB_REQUIRE((reinterpret_cast<uintptr_t>(t.tiles) & 15) == 0 && t.kind_stride % 16 == 0 && t.head_stride % 16 == 0,
+              "osb_gemm_head_tiles: tile buffer must be 16-byte aligned");
+  OSB_REQUIRE(a.bias == nullptr || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0, "osb_gemm_head_tiles: bias must be 16-byte aligned");
+  const int dp = (D + 15) / 16 * 16;
+  const int64_t tile_bytes = (int64_t)m.tile_rows * dp * 2;
+  const int64_t tph = osb_head_tiles_per_head(&m, a.M);
+  OSB_REQUIRE(t.head_stride >= tph * tile_bytes, "osb_gemm_head_tiles: head_stride %lld < %lld tiles of %lld bytes",
+              (long long)t.head_stride, (long long)tph, (long long)tile_bytes);
+  HeadTileParams ht = {};
+  ht.base = static_cast<uint8_t*>(t.tiles);
+  ht.kind_stride = t.kind_stride; ht.head_stride = t.head_stride;
+  ht.map.mode = m.mode; ht.map.L = m.L; ht.map.S = m.S; ht.map.T = m.T; ht.map.G = m.G; ht.map.tps = m.tps; ht.map.TR = m.tile_rows;
+  ht.tile_bytes = (int32_t)tile_bytes;
+  ht.heads = t.num_heads; ht.nkinds = t.nkinds;
+  ht.norm_mask = t.norm_mask; ht.rope_mask = t.rope_mask;
+  for (int k = 0; k < 4; ++k) {
+    ht.norm_w[k] = static_cast<const __nv_bfloat16*>(t.norm_w[k]);
+    OSB_REQUIRE(!((t.norm_mask >> k) & 1u) || (k < t.nkinds && t.norm_w[k] != nullptr && (reinterpret_cast<uintptr_t>(t.norm_w[k]) & 15) == 0),
+                "osb_gemm_head_tiles: kind %d has RMSNorm enabled but no (16-byte aligned) weight", k);
+  }
+  ht.eps = t.norm_eps;
+  ht.cos = t.rope_cos; ht.sin = t.rope_sin;
+  OSB_REQUIRE(t.rope_mask == 0 || (t.rope_cos && t.rope_sin && ((reinterpret_cast<uintptr_t>(t.rope_cos) | reinterpret_cast<uintptr_t>(t.rope_sin)) & 15) == 0),
+              "osb_gemm_head_tiles: RoPE enabled but the cos / sin tables are missing or not 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (D == 64) return launch_gemm_ht<64>(a, ht, s);
+  if (D == 72) return launch_gemm_ht<72>(a, ht, s);
+  return launch_gemm_ht<128>(a, ht, s);
 }

@@ -10,10 +10,13 @@ short-KV tcgen05 attention with fused QK-RMSNorm + RoPE, the LN+modulate row ker
 CPU or eager fallback: calling forward on a non-CUDA / non-bf16 model raises.
 
 Per block (SURVEY.md §8a-S `STDiT3Block.forward`), 10 launches:
-  ln_modulate -> qkv GEMM -> attention(+RMSNorm,+RoPE) -> proj GEMM (+gate, +residual)
-  -> q GEMM -> cross attention (kv_lens) -> proj GEMM (+residual)
+  ln_modulate -> qkv GEMM (+bias, +QK-RMSNorm, +RoPE, stored as attention operand tiles) -> attention
+  -> proj GEMM (+gate, +residual) -> q GEMM (operand tiles) -> cross attention (kv_lens) -> proj GEMM (+residual)
   -> ln_modulate -> fc1 GEMM (+GELU-tanh) -> fc2 GEMM (+gate, +residual)
 The 2*depth kv_linear projections of the (block-invariant) text tokens are batched into one GEMM.
+q / k / v never exist in token layout: the projection epilogue writes "head tiles" (include/osb200.h) that the
+attention kernel loads with one bulk copy per tile.  Head sizes the tile path is not built for (anything but
+64 / 72 / 128, or an odd head count) use the register-path kernel `osb_attn_short` on token-layout q / k / v.
 """
 from __future__ import annotations
 
@@ -351,7 +354,12 @@ class STDiT3(nn.Module):
         yp = self.y_embedder.y_proj
         yh = osb.gemm(yt, yp.fc1.weight, yp.fc1.bias, epilogue=osb.EPI_BIAS_GELU_TANH)
         ye = osb.gemm(yh, yp.fc2.weight, yp.fc2.bias)                                    # [B*Ly, C]
-        kv_all = osb.gemm(ye, cst["kv_w"], cst["kv_b"])                                  # [B*Ly, nb*2C]
+        use_tiles = self._use_tiles()
+        if use_tiles:   # keys / values of all 2*depth blocks as attention operand tiles: [block][k|v][head][tile]
+            kv_all = self._tiles(osb, ("kv", B, Ly), B * Ly, osb.tile_map(0, Ly, keys_only=True), 2 * nb, dev)
+            osb.gemm_head_tiles(ye, cst["kv_w"], cst["kv_b"], kv_all, nkinds=2)
+        else:
+            kv_all = osb.gemm(ye, cst["kv_w"], cst["kv_b"])                              # [B*Ly, nb*2C]
         if mask is not None:
             m2 = mask.to(dev)
             if m2.shape[0] != B:
@@ -374,19 +382,24 @@ class STDiT3(nn.Module):
         # ---- workspaces reused by every block ------------------------------------------------------
         R = B * N
         xm_buf = torch.empty(R, C, dtype=bf, device=dev)
-        qkv = torch.empty(R, 3 * C, dtype=bf, device=dev)
         ao = torch.empty(R, C, dtype=bf, device=dev)
-        qc = torch.empty(R, C, dtype=bf, device=dev)
         hid = torch.empty(R, int(C * self.config.mlp_ratio), dtype=bf, device=dev)
         cos, sin = self._rope(T, dev)
-        mstride = mod.stride(0)
+        ws = dict(xm=xm_buf, ao=ao, hid=hid, cos=cos, sin=sin, kv=kv_all, kv_lens=kv_lens, tiles=use_tiles)
+        if use_tiles:
+            Sl = S // P   # temporal attention runs on this rank's S/P columns of every frame
+            ws["sp_t"] = self._tiles(osb, ("spatial", B, Tl, S), R, osb.tile_map(0, S), 3, dev)
+            ws["tm_t"] = self._tiles(osb, ("temporal", B, T, Sl), B * T * Sl, osb.tile_map(1, T, Sl, T), 3, dev)
+            ws["q_t"] = self._tiles(osb, ("crossq", B, N), R, osb.tile_map(0, N, pack=False), 1, dev)
+        else:
+            ws["qkv"] = torch.empty(R, 3 * C, dtype=bf, device=dev)
+            ws["qc"] = torch.empty(R, C, dtype=bf, device=dev)
 
         bi = 0
         for sb, tb in zip(self.spatial_blocks, self.temporal_blocks):
             for blk in (sb, tb):
                 m = mod[:, bi]  # [B', 6, C] view, row stride = mod.stride(0)
-                self._block(osb, blk, xs, m, mod_index, group_rows, kv_all[:, bi * 2 * C:(bi + 1) * 2 * C], kv_lens, Ly,
-                            B, T, Tl, S, xm_buf, qkv, ao, qc, hid, cos, sin, sp if P > 1 else None)
+                self._block(osb, blk, bi, xs, m, mod_index, group_rows, Ly, B, T, Tl, S, ws, sp if P > 1 else None)
                 bi += 1
 
         # ---- final layer + unpatchify -----------------------------------------------------------------
@@ -405,13 +418,26 @@ class STDiT3(nn.Module):
         o = o.reshape(B, self.out_channels, T * pt, H * ph, W * pw)[:, :, :Tx, :Hx, :Wx]
         return o.to(torch.float32)
 
-    def _block(self, osb, blk, xs, m, mod_index, group_rows, kv, kv_lens, Ly, B, T, Tl, S, xm_buf, qkv, ao, qc, hid, cos,
-               sin, sp):
+    def _use_tiles(self) -> bool:
+        """The head-tile attention path (osb_gemm_head_tiles + osb_attn_tiles) is built for head sizes 64 / 72 / 128 and an
+        even head count; OSB_ATTN_TILES=0 forces the register-path kernel (A/B measurements)."""
+        return (self.head_dim in (64, 72, 128) and self.num_heads % 2 == 0
+                and os.environ.get("OSB_ATTN_TILES", "1") != "0")
+
+    def _tiles(self, osb, key, rows, tmap, kinds, dev):
+        """Tile workspaces are cached per shape: they are zero-filled once (rows no token maps to must stay finite)."""
+        key = ("tiles", key, tmap.key(), kinds, dev)
+        if key not in self._cache:
+            self._cache[key] = osb.HeadTiles(rows, tmap, kinds, self.num_heads, self.head_dim, dev)
+        return self._cache[key]
+
+    def _block(self, osb, blk, bi, xs, m, mod_index, group_rows, Ly, B, T, Tl, S, ws, sp):
         C, Hh, D = self.hidden_size, self.num_heads, self.head_dim
         N = Tl * S
         a, ca, mlp = blk.attn, blk.cross_attn, blk.mlp
         qn = a.q_norm.weight if isinstance(a.q_norm, _Norm) else None
         kn = a.k_norm.weight if isinstance(a.k_norm, _Norm) else None
+        xm_buf, ao, hid, cos, sin, tiles = ws["xm"], ws["ao"], ws["hid"], ws["cos"], ws["sin"], ws["tiles"]
         # 1. self attention (spatial: sequences over S; temporal: sequences over T with RoPE)
         osb.ln_modulate(xs, m[:, 0], m[:, 1], group_rows=group_rows, mod_index=mod_index, out=xm_buf)
         if blk.temporal:
@@ -424,15 +450,27 @@ class STDiT3(nn.Module):
                 xt = all_to_all(xm_buf.view(B, Tl, S, C), sp, scatter_dim=2, gather_dim=1).view(B * T * Sl, C)
             else:
                 Sl, xt = S, xm_buf
-            osb.gemm(xt, a.qkv.weight, a.qkv.bias, out=qkv)
-            strides = (T * Sl, 1, Sl)
             ao_t = ao if sp is None else torch.empty_like(ao)
-            osb.attn_short(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], ao_t, num_seqs=B * Sl, seqs_per_batch=Sl,
-                           q_strides=strides, k_strides=strides, Lq=T, Lk=T, num_heads=Hh, head_dim=D,
-                           q_norm_w=qn, k_norm_w=kn, rope_cos=cos, rope_sin=sin)
+            if tiles:
+                tt = ws["tm_t"]
+                osb.gemm_head_tiles(xt, a.qkv.weight, a.qkv.bias, tt, nkinds=3, norm_w=(qn, kn, None), rope=(cos, sin),
+                                    rope_kinds=0b011)
+                osb.attn_tiles(tt, tt, ao_t, Lk=T, num_seqs=B * Sl)
+            else:
+                qkv = ws["qkv"]
+                osb.gemm(xt, a.qkv.weight, a.qkv.bias, out=qkv)
+                strides = (T * Sl, 1, Sl)
+                osb.attn_short(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], ao_t, num_seqs=B * Sl, seqs_per_batch=Sl,
+                               q_strides=strides, k_strides=strides, Lq=T, Lk=T, num_heads=Hh, head_dim=D,
+                               q_norm_w=qn, k_norm_w=kn, rope_cos=cos, rope_sin=sin)
             if sp is not None:
                 ao = all_to_all(ao_t.view(B, T, Sl, C), sp, scatter_dim=1, gather_dim=2).view(B * N, C)
+        elif tiles:
+            st = ws["sp_t"]
+            osb.gemm_head_tiles(xm_buf, a.qkv.weight, a.qkv.bias, st, nkinds=3, norm_w=(qn, kn, None))
+            osb.attn_tiles(st, st, ao, Lk=S, num_seqs=B * Tl)
         else:
+            qkv = ws["qkv"]
             osb.gemm(xm_buf, a.qkv.weight, a.qkv.bias, out=qkv)
             strides = (N, S, 1)
             osb.attn_short(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], ao, num_seqs=B * Tl, seqs_per_batch=Tl,
@@ -441,9 +479,18 @@ class STDiT3(nn.Module):
         osb.gemm(ao, a.proj.weight, a.proj.bias, epilogue=osb.EPI_BIAS_GATE_RES, residual=xs, gate=m[:, 2],
                  group_rows=group_rows, mod_index=mod_index, out=xs)
         # 2. cross attention over the T5 tokens (plain residual)
-        osb.gemm(xs, ca.q_linear.weight, ca.q_linear.bias, out=qc)
-        osb.attn_short(qc, kv[:, :C], kv[:, C:], ao, num_seqs=B, seqs_per_batch=1, q_strides=(N, 0, 1),
-                       k_strides=(Ly, 0, 1), Lq=N, Lk=Ly, num_heads=Hh, head_dim=D, kv_lens=kv_lens)
+        ao = ws["ao"]
+        if tiles:
+            qt = ws["q_t"]
+            osb.gemm_head_tiles(xs, ca.q_linear.weight, ca.q_linear.bias, qt, nkinds=1)
+            osb.attn_tiles(qt, ws["kv"], ao, q_kind=0, k_kind=2 * bi, v_kind=2 * bi + 1, Lk=Ly, num_seqs=B,
+                           kv_lens=ws["kv_lens"])
+        else:
+            qc = ws["qc"]
+            kv = ws["kv"][:, bi * 2 * C:(bi + 1) * 2 * C]
+            osb.gemm(xs, ca.q_linear.weight, ca.q_linear.bias, out=qc)
+            osb.attn_short(qc, kv[:, :C], kv[:, C:], ao, num_seqs=B, seqs_per_batch=1, q_strides=(N, 0, 1),
+                           k_strides=(Ly, 0, 1), Lq=N, Lk=Ly, num_heads=Hh, head_dim=D, kv_lens=ws["kv_lens"])
         osb.gemm(ao, ca.proj.weight, ca.proj.bias, epilogue=osb.EPI_BIAS_GATE_RES, residual=xs, gate=None, out=xs)
         # 3. MLP
         osb.ln_modulate(xs, m[:, 3], m[:, 4], group_rows=group_rows, mod_index=mod_index, out=xm_buf)

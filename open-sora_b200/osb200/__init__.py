@@ -26,6 +26,10 @@ EXPORTS = (
     "osb_group_stats_workspace_bytes",
     "osb_vae_prep",
     "osb_cfg_euler",
+    "osb_gemm_head_tiles",
+    "osb_head_tiles_per_head",
+    "osb_attn_tiles",
+    "osb_tmap_cache_stats",
 )
 
 EPI_BIAS, EPI_BIAS_GELU_TANH, EPI_BIAS_GATE_RES = 0, 1, 2
@@ -63,6 +67,12 @@ def _load() -> C.CDLL:
                                     C.c_int64, C.c_void_p, C.c_void_p]
     lib.osb_group_stats_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int32]
     lib.osb_group_stats_workspace_bytes.restype = C.c_int64
+    lib.osb_gemm_head_tiles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.osb_attn_tiles.argtypes = [C.c_void_p, C.c_void_p]
+    lib.osb_head_tiles_per_head.argtypes = [C.c_void_p, C.c_int64]
+    lib.osb_head_tiles_per_head.restype = C.c_int64
+    lib.osb_tmap_cache_stats.argtypes = [C.c_void_p, C.c_void_p]
+    lib.osb_tmap_cache_stats.restype = None
     return lib
 
 
@@ -311,6 +321,139 @@ def attn_short(q, k, v, out, *, num_seqs: int, seqs_per_batch: int, q_strides, k
     with _Timed("attn_short", 4.0 * num_seqs * Lq * Lk * num_heads * head_dim):  # QK^T + PV FLOPs
         _check(_lib.osb_attn_short(C.byref(a), _stream()), "osb_attn_short")
     return out
+
+
+# ---- head tiles: projection GEMM -> attention without a layout pass (include/osb200.h) ------------------------------
+class TileMap(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("L", C.c_int32), ("S", C.c_int32), ("T", C.c_int32), ("G", C.c_int32),
+                ("tps", C.c_int32), ("tile_rows", C.c_int32), ("reserved", C.c_int32)]
+
+    def key(self):
+        return (self.mode, self.L, self.S, self.T, self.G, self.tps, self.tile_rows)
+
+
+class HeadTilesArgs(C.Structure):
+    _fields_ = [
+        ("tiles", C.c_void_p), ("kind_stride", C.c_int64), ("head_stride", C.c_int64), ("map", TileMap),
+        ("num_heads", C.c_int32), ("head_dim", C.c_int32), ("nkinds", C.c_int32),
+        ("norm_mask", C.c_uint32), ("rope_mask", C.c_uint32), ("reserved", C.c_int32),
+        ("norm_w", C.c_void_p * 4), ("norm_eps", C.c_float), ("reserved2", C.c_int32),
+        ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
+    ]
+
+
+class AttnTilesArgs(C.Structure):
+    _fields_ = [
+        ("q_tiles", C.c_void_p), ("k_tiles", C.c_void_p), ("v_tiles", C.c_void_p),
+        ("q_head_stride", C.c_int64), ("kv_head_stride", C.c_int64), ("q_map", TileMap),
+        ("kv_tile_rows", C.c_int32), ("kv_tiles_per_set", C.c_int32), ("Lk", C.c_int32),
+        ("num_heads", C.c_int32), ("head_dim", C.c_int32), ("reserved", C.c_int32),
+        ("num_seqs", C.c_int64), ("kv_lens", C.c_void_p), ("out", C.c_void_p), ("out_ld", C.c_int64),
+        ("softmax_scale", C.c_float), ("reserved2", C.c_int32),
+    ]
+
+
+def tile_map(mode: int, L: int, S: int = 0, T: int = 0, *, keys_only: bool = False, pack: bool = True) -> TileMap:
+    """Token row -> (tile, row) map of include/osb200.h `osb_tile_map`.  mode 0: sequences are contiguous blocks of L
+    rows; mode 1: sequences run along T of a frame-major [B, T, S] token stream (L == T).  Short sequences (L <= 64) are
+    packed 128 // L per tile (self-attention: a tile is its own key set; `pack=False` for cross-attention queries,
+    whose key set is per sequence); `keys_only` (text keys of cross-attention) balances the tiles instead:
+    ceil(L / 128) tiles of equal size."""
+    m = TileMap()
+    m.mode, m.L, m.S, m.T = mode, L, S, T
+    if L <= 64 and pack and not keys_only:
+        m.G, m.tps = 128 // L, 1
+        m.tile_rows = -(-(m.G * L) // 16) * 16
+    else:
+        m.G = 1
+        n = -(-L // 128)
+        m.tile_rows = 128 if (L > 128 and not keys_only) else -(-(-(-L // n)) // 16) * 16
+        m.tps = -(-L // m.tile_rows)
+    return m
+
+
+class HeadTiles:
+    """A buffer of head tiles: `kinds` column groups (q | k | v ...) x heads x tiles.  Zero-initialised: rows no token
+    maps to (ragged last tile, head-dim tail) must stay finite, they are multiplied by P = 0 in the PV product."""
+
+    def __init__(self, rows: int, tmap: TileMap, kinds: int, heads: int, head_dim: int, device):
+        import torch
+
+        self.rows, self.map, self.kinds, self.heads, self.head_dim = rows, tmap, kinds, heads, head_dim
+        self.tiles_per_head = int(_lib.osb_head_tiles_per_head(C.byref(tmap), rows))
+        if self.tiles_per_head <= 0:
+            raise OsbError(f"tile map {tmap.key()} does not fit {rows} rows")
+        self.tile_bytes = tmap.tile_rows * (-(-head_dim // 16) * 16) * 2
+        self.head_stride = self.tiles_per_head * self.tile_bytes
+        self.kind_stride = heads * self.head_stride
+        self.buf = torch.zeros(kinds * self.kind_stride, dtype=torch.uint8, device=device)
+
+    def kind_ptr(self, kind: int) -> int:
+        return self.buf.data_ptr() + kind * self.kind_stride
+
+
+def gemm_head_tiles(a, w, bias, tiles: HeadTiles, *, nkinds: int, norm_w=(), rope=None, rope_kinds: int = 0,
+                    eps: float = 1e-6, kind0: int = 0):
+    """tiles[kind0 + n // C] = head_tiles(a @ w.T + bias): each output row is split into heads; kinds listed in
+    `norm_w` (bf16 [D] or None per kind) get per-head RMSNorm, kinds in the `rope_kinds` bit mask get interleaved-pair
+    RoPE by token position from `rope` = (cos, sin) fp32 [L, D/2]; one rounding to bf16 at the row's place in its tile."""
+    import torch
+
+    _need(a, torch.bfloat16, "a"); _need(w, torch.bfloat16, "w"); _need(bias, torch.bfloat16, "bias")
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
+    M, K = a.shape
+    N = w.shape[0]
+    Cc = tiles.heads * tiles.head_dim
+    assert M == tiles.rows and N % Cc == 0 and kind0 + N // Cc <= tiles.kinds
+    g = GemmArgs()
+    g.A, g.W, g.bias = a.data_ptr(), w.data_ptr(), (bias.data_ptr() if bias is not None else None)
+    g.M, g.N, g.K = M, N, K
+    g.lda, g.ldw = a.stride(0), w.stride(0)
+    t = HeadTilesArgs()
+    t.tiles = tiles.kind_ptr(kind0)
+    t.kind_stride, t.head_stride, t.map = tiles.kind_stride, tiles.head_stride, tiles.map
+    t.num_heads, t.head_dim, t.nkinds = tiles.heads, tiles.head_dim, nkinds
+    mask = 0
+    for i, nw in enumerate(norm_w):
+        if nw is not None:
+            _need(nw, torch.bfloat16, "norm_w")
+            t.norm_w[i] = nw.data_ptr()
+            mask |= 1 << i
+    t.norm_mask, t.rope_mask, t.norm_eps = mask, (rope_kinds if rope is not None else 0), eps
+    if rope is not None:
+        _need(rope[0], torch.float32, "rope cos"); _need(rope[1], torch.float32, "rope sin")
+        t.rope_cos, t.rope_sin = rope[0].data_ptr(), rope[1].data_ptr()
+    with _Timed("gemm", 2.0 * M * N * K):
+        _check(_lib.osb_gemm_head_tiles(C.byref(g), C.byref(t), _stream()), "osb_gemm_head_tiles")
+    return tiles
+
+
+def attn_tiles(q: HeadTiles, kv: HeadTiles, out, *, q_kind: int = 0, k_kind: int = 1, v_kind: int = 2, Lk: int,
+               num_seqs: int, kv_lens=None, softmax_scale: float | None = None):
+    """out = softmax(q k^T * scale) v per (sequence, head) over head tiles (osb_attn_tiles).  Self-attention: q and kv
+    are the same buffer (kinds 0, 1, 2); cross-attention: kv holds the text keys / values (`keys_only` map)."""
+    import torch
+
+    _need(out, torch.bfloat16, "out"); _need(kv_lens, torch.int32, "kv_lens")
+    a = AttnTilesArgs()
+    a.q_tiles, a.k_tiles, a.v_tiles = q.kind_ptr(q_kind), kv.kind_ptr(k_kind), kv.kind_ptr(v_kind)
+    a.q_head_stride, a.kv_head_stride, a.q_map = q.head_stride, kv.head_stride, q.map
+    a.kv_tile_rows = kv.map.tile_rows
+    a.kv_tiles_per_set = kv.map.tps
+    a.Lk, a.num_heads, a.head_dim = Lk, q.heads, q.head_dim
+    a.num_seqs = num_seqs
+    a.kv_lens = kv_lens.data_ptr() if kv_lens is not None else None
+    a.out, a.out_ld = out.data_ptr(), out.stride(0)
+    a.softmax_scale = softmax_scale if softmax_scale is not None else q.head_dim ** -0.5
+    with _Timed("attn_tiles", 4.0 * num_seqs * q.map.L * Lk * q.heads * q.head_dim):
+        _check(_lib.osb_attn_tiles(C.byref(a), _stream()), "osb_attn_tiles")
+    return out
+
+
+def tmap_cache_stats():
+    h, m = C.c_int64(0), C.c_int64(0)
+    _lib.osb_tmap_cache_stats(C.byref(h), C.byref(m))
+    return int(h.value), int(m.value)
 
 
 # ---- causal 3D VAE ops (NDHWC) -------------------------------------------------------------------------

@@ -291,3 +291,100 @@ def cfg_euler(cond, uncond, uncond2, x, *, g_txt: float, g_img: float = 1.0, g_i
         return y
     out.copy_(y)
     return out
+
+
+# ---- head tiles (include/osb200.h osb_gemm_head_tiles / osb_attn_tiles): the double keeps the tile buffer as a dense
+# [kinds, rows, heads*D] tensor - the byte layout of a tile is the kernels' business, the CONTRACT is which token row and
+# head a value belongs to, what was applied to it (bias, RMSNorm, RoPE by position) and which keys a query may see. ------
+class TileMap:
+    def __init__(self):
+        self.mode = self.L = self.S = self.T = self.G = self.tps = self.tile_rows = 0
+
+    def key(self):
+        return (self.mode, self.L, self.S, self.T, self.G, self.tps, self.tile_rows)
+
+
+def tile_map(mode: int, L: int, S: int = 0, T: int = 0, *, keys_only: bool = False, pack: bool = True) -> TileMap:
+    m = TileMap()
+    m.mode, m.L, m.S, m.T = mode, L, S, T
+    if L <= 64 and pack and not keys_only:
+        m.G, m.tps = 128 // L, 1
+        m.tile_rows = -(-(m.G * L) // 16) * 16
+    else:
+        m.G = 1
+        n = -(-L // 128)
+        m.tile_rows = 128 if (L > 128 and not keys_only) else -(-(-(-L // n)) // 16) * 16
+        m.tps = -(-L // m.tile_rows)
+    return m
+
+
+class HeadTiles:
+    def __init__(self, rows, tmap, kinds, heads, head_dim, device):
+        if tmap.mode == 0:
+            assert rows % tmap.L == 0, "rows must be whole sequences"
+        else:
+            assert tmap.T == tmap.L and tmap.S > 0 and rows % (tmap.S * tmap.T) == 0
+        self.rows, self.map, self.kinds, self.heads, self.head_dim = rows, tmap, kinds, heads, head_dim
+        self.dense = torch.zeros(kinds, rows, heads * head_dim, dtype=torch.bfloat16, device=device)
+
+
+def _seq_pos(m, rows, device):
+    r = torch.arange(rows, device=device)
+    if m.mode == 0:
+        return r // m.L, r % m.L
+    b, rem = r // (m.T * m.S), r % (m.T * m.S)
+    return b * m.S + rem % m.S, rem // m.S
+
+
+def gemm_head_tiles(a, w, bias, tiles, *, nkinds, norm_w=(), rope=None, rope_kinds=0, eps=1e-6, kind0=0):
+    for t, n in ((a, "a"), (w, "w"), (bias, "bias")):
+        _need(t, torch.bfloat16, n)
+    M, K = a.shape
+    N = w.shape[0]
+    H, D = tiles.heads, tiles.head_dim
+    Cc = H * D
+    assert M == tiles.rows and N % Cc == 0 and kind0 + N // Cc <= tiles.kinds and a.shape[1] == w.shape[1]
+    if D not in (64, 72, 128) or H % 2:
+        raise OsbError("osb_gemm_head_tiles failed (-1): head_dim / head count not built")
+    acc = a.float() @ w.float().t()
+    if bias is not None:
+        acc = acc + bias.float()
+    _, pos = _seq_pos(tiles.map, M, a.device)
+    for kidx in range(N // Cc):
+        kind = kidx % nkinds
+        x = acc[:, kidx * Cc:(kidx + 1) * Cc].reshape(M, H, D)
+        nw = norm_w[kind] if kind < len(norm_w) else None
+        if nw is not None:
+            x = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * nw.float()
+        if rope is not None and (rope_kinds >> kind) & 1:
+            c, s_ = rope[0][pos][:, None, :], rope[1][pos][:, None, :]
+            xa, xb = x[..., 0::2], x[..., 1::2]
+            x = torch.stack((xa * c - xb * s_, xb * c + xa * s_), dim=-1).reshape(M, H, D)
+        tiles.dense[kind0 + kidx] = x.reshape(M, Cc).to(torch.bfloat16)
+    _count("gemm", (M, N, K, "head_tiles"))
+    return tiles
+
+
+def attn_tiles(q, kv, out, *, q_kind=0, k_kind=1, v_kind=2, Lk, num_seqs, kv_lens=None, softmax_scale=None):
+    H, D = q.heads, q.head_dim
+    m = q.map
+    scale = softmax_scale if softmax_scale is not None else D ** -0.5
+    seq_q, _ = _seq_pos(m, q.rows, out.device)
+    seq_k, pos_k = _seq_pos(kv.map, kv.rows, out.device)
+    assert int(seq_q.max()) + 1 == num_seqs
+    for s in range(num_seqs):
+        rq = (seq_q == s).nonzero().flatten()
+        rk = (seq_k == s).nonzero().flatten()
+        rk = rk[pos_k[rk].argsort()]
+        n = Lk if kv_lens is None else min(int(kv_lens[s]), Lk)
+        if n <= 0:
+            out[rq] = 0
+            continue
+        rk = rk[:n]
+        qq = q.dense[q_kind][rq].float().view(-1, H, D).permute(1, 0, 2)
+        kk = kv.dense[k_kind][rk].float().view(-1, H, D).permute(1, 0, 2)
+        vv = kv.dense[v_kind][rk].float().view(-1, H, D).permute(1, 0, 2)
+        pr = torch.softmax(qq @ kk.transpose(-1, -2) * scale, dim=-1).to(torch.bfloat16).float()
+        out[rq] = (pr @ vv).permute(1, 0, 2).reshape(len(rq), H * D).to(torch.bfloat16)
+    _count("attn_tiles", (num_seqs, m.L, Lk, H, D))
+    return out

@@ -40,7 +40,7 @@ def test_forward_matches_oracle(fake_osb, B, T, H, W):
     # the boundary was driven as designed: every Linear is a gemm call, 3 attention calls and 2 LN calls per block + final LN
     names = [c[0] for c in fake_osb.calls]
     nb = 2 * cfg.depth
-    assert names.count("attn_short") == 2 * nb and names.count("ln_modulate") == 2 * nb + 1
+    assert names.count("attn_tiles") + names.count("attn_short") == 2 * nb and names.count("ln_modulate") == 2 * nb + 1
     kv = [c for c in fake_osb.calls if c[0] == "gemm" and c[1][1] == nb * 2 * cfg.hidden_size]
     assert len(kv) == 1, "all blocks' kv_linear run as ONE GEMM"
 
