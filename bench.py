@@ -95,10 +95,11 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (restatement of the reference arithmetic) on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step(sample_seconds_budget: float = 20.0):
+def cpu_reference_step(sample_seconds_budget: float = 30.0, repeats: int = 3):
     """Times ONE spatial+temporal block pair of the fp32 oracle at the full 16384 tokens plus the
     embedders/final layer, and extrapolates to the 28 pairs of a step (linear in depth, exact: the
-    blocks are identical in shape).  Returns (steps_per_s, cores, sample description)."""
+    blocks are identical in shape).  One untimed warm-up pass (thread pool, allocator, page faults), then the
+    MEDIAN of `repeats` timings (bounded by the budget).  Returns (steps_per_s, cores, sample description)."""
     from oracle import stdit3_oracle as O
 
     cores = os.cpu_count() or 1
@@ -108,23 +109,77 @@ def cpu_reference_step(sample_seconds_budget: float = 20.0):
     m = O.STDiT3(cfg).eval()
     O.init_synthetic_weights(m)
     inp = O.synthetic_inputs(cfg, 1, T_LAT, H_LAT, W_LAT)
+    B, T, S, C = 1, T_LAT, (H_LAT // 2) * (W_LAT // 2), cfg.hidden_size
     with torch.no_grad():
-        t0 = time.perf_counter()
-        m(**inp)
-        t_full1 = time.perf_counter() - t0  # depth-1 model: embed + 1 pair + final
-        # isolate the pair: time the two blocks alone on the embedded tokens
-        B, T, S, C = 1, T_LAT, (H_LAT // 2) * (W_LAT // 2), cfg.hidden_size
-        x = torch.randn(B, T * S, C)
-        t_mlp = torch.randn(B, 6 * C)
         y, y_lens = m.encode_text(inp["y"], inp["mask"])
+        x0 = torch.randn(B, T * S, C)
+        t_mlp = torch.randn(B, 6 * C)
+
+        def pair():
+            t0 = time.perf_counter()
+            x = m.spatial_blocks[0](x0, y, t_mlp, y_lens, None, None, T, S)
+            m.temporal_blocks[0](x, y, t_mlp, y_lens, None, None, T, S)
+            return time.perf_counter() - t0
+
+        t_start = time.perf_counter()
+        pair()                                   # warm-up, untimed
+        ts = []
+        for _ in range(repeats):
+            ts.append(pair())
+            if time.perf_counter() - t_start > sample_seconds_budget:
+                break
+        ts.sort()
+        t_pair = ts[len(ts) // 2]
         t0 = time.perf_counter()
-        x = m.spatial_blocks[0](x, y, t_mlp, y_lens, None, None, T, S)
-        x = m.temporal_blocks[0](x, y, t_mlp, y_lens, None, None, T, S)
-        t_pair = time.perf_counter() - t0
+        m(**inp)                                 # depth-1 model: embed + 1 pair + final (warm by now)
+        t_full1 = time.perf_counter() - t0
     t_other = max(t_full1 - t_pair, 0.0)
     step_s = 28 * t_pair + t_other
-    return 1.0 / step_s, cores, (f"1 of 28 spatial+temporal block pairs of the fp32 oracle timed at the full 16384 tokens "
-                                 f"({t_pair:.2f}s) + embedders/final ({t_other:.2f}s), x28 extrapolated")
+    return 1.0 / step_s, cores, (f"1 of 28 spatial+temporal block pairs of the fp32 oracle at the full 16384 tokens: median of "
+                                 f"{len(ts)} after a warm-up ({t_pair:.2f}s, spread {ts[0]:.2f}-{ts[-1]:.2f}s) + embedders/final "
+                                 f"({t_other:.2f}s), x28 extrapolated")
+
+
+def library_baseline_step(dev, steps: int = 3):
+    """Same-box reference point other than a CPU: the oracle's plain-PyTorch STDiT3 in bf16 on the GPU -
+    cuBLAS GEMMs + torch SDPA + eager elementwise kernels, i.e. what the reference's own stack does without osb200.
+    One block PAIR at the full 16384 tokens is timed with CUDA events and extrapolated x28 like the CPU arm (a full
+    1.1 B-parameter second model next to the product would not change the number, only the memory footprint)."""
+    from oracle import stdit3_oracle as O
+
+    cfg = O.STDiT3_XL_2_config()
+    cfg.depth = 1
+    with torch.device(dev):
+        m = O.STDiT3(cfg).eval()
+    O.init_synthetic_weights(m)
+    m = m.to(device=dev, dtype=torch.bfloat16)
+    inp = O.synthetic_inputs(cfg, 1, T_LAT, H_LAT, W_LAT)
+    inp = {k: (v.to(torch.bfloat16) if v.is_floating_point() else v).to(dev) for k, v in inp.items()}
+    B, T, S, C = 1, T_LAT, (H_LAT // 2) * (W_LAT // 2), cfg.hidden_size
+    with torch.no_grad():
+        y, y_lens = m.encode_text(inp["y"], inp["mask"])
+        x0 = torch.randn(B, T * S, C, device=dev, dtype=torch.bfloat16)
+        t_mlp = torch.randn(B, 6 * C, device=dev, dtype=torch.bfloat16)
+
+        def pair():
+            x = m.spatial_blocks[0](x0, y, t_mlp, y_lens, None, None, T, S)
+            return m.temporal_blocks[0](x, y, t_mlp, y_lens, None, None, T, S)
+
+        for _ in range(3):
+            pair()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            pair()
+        e.record()
+        torch.cuda.synchronize()
+        ms_pair = s.elapsed_time(e) / steps
+    del m
+    torch.cuda.empty_cache()
+    return {"value": 1e3 / (28 * ms_pair), "unit": UNIT, "ms_per_step": 28 * ms_pair,
+            "kind": "plain PyTorch bf16 on the same GPU (cuBLAS + SDPA + eager elementwise), the oracle's module code",
+            "sample": f"1 of 28 block pairs at 16384 tokens ({ms_pair:.2f} ms, CUDA events, 3 warm-ups), x28; embedders excluded"}
 
 
 def run_reference(args, rank):
@@ -230,12 +285,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="osb200", choices=["osb200", "reference"])
-    ap.add_argument("--parallel", default="dp", choices=["sp", "dp"],
-                    help="N>1: dp = one independent sample per rank, no data-path collective (weak scaling; the batch "
-                         "axis of north_star's 'batch x T' sharding); sp = ONE sample sequence-sharded over the ranks "
-                         "with all-to-all at the spatial<->temporal boundary (strong scaling)")
+    ap.add_argument("--parallel", default="sp", choices=["sp", "dp"],
+                    help="N>1: sp (default) = ONE sample sequence-sharded over the ranks, exchange at the spatial<->temporal "
+                         "boundary (north_star's partition; strong scaling; the dp replica rate is reported beside it as "
+                         "`dp_replicas`); dp = one independent sample per rank, no data-path collective (weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", action="store_true", help="replay the step as one CUDA graph (model.capture)")
+    ap.add_argument("--graph", dest="graph", action="store_true", default=None,
+                    help="replay the step as one CUDA graph (model.capture); default: on for sp, off otherwise")
+    ap.add_argument("--no-graph", dest="graph", action="store_false")
+    ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--no-vae", action="store_true", help="skip the VAE leg (encode/decode fps of BASELINE.json's metric)")
     ap.add_argument("--profile-step", action="store_true",
                     help="after warm-up, bracket ONE step with cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`: "
@@ -261,10 +319,26 @@ def main():
     osb200.init(local_rank)
     model = build_model(dev)
     mode = args.parallel if world > 1 else "single"
-    if mode == "sp":
-        model.enable_sequence_parallel(dist.group.WORLD)
+    if args.graph is None:
+        args.graph = mode == "sp"   # 2 048 tokens per rank at N = 8: the step is launch-bound without a graph
     hin = host_inputs(4321 + (rank if mode == "dp" else 0))
     din = {k: v.to(dev, non_blocking=True) for k, v in hin.items()}
+    sp_check = None
+    if mode == "sp":
+        # in-run parity of the partition: the sequence-parallel forward against the SAME model's single-GPU forward
+        with torch.no_grad():
+            single = model(**din).clone()
+            model.enable_sequence_parallel(dist.group.WORLD)
+            spo = model(**din)
+        torch.cuda.synchronize()
+        diff = (spo.double() - single.double())
+        sp_check = {"sp_matches_single_gpu": bool(torch.equal(spo, single)),
+                    "max_abs": float(diff.abs().max()), "rel_l2": float(diff.norm() / single.double().norm()),
+                    "ref_absmax": float(single.abs().max())}
+        flag = torch.tensor([1.0 if sp_check["rel_l2"] < 2e-3 else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        sp_check["all_ranks_ok"] = bool(flag.item() == 1.0)
+        del single, spo
 
     def barrier():
         if world > 1:
@@ -344,6 +418,23 @@ def main():
     units = args.steps * (world if mode == "dp" else 1)
     value = units / (ms / 1e3)
     e2e = units / (ms_e2e / 1e3)
+
+    # sp runs also report the replica rate (one independent sample per rank, no collective): the weak-scaling number
+    dp_extra = None
+    if mode == "sp":
+        model.enable_sequence_parallel(None)
+        hin_dp = host_inputs(4321 + rank)
+        din_dp = {k: v.to(dev, non_blocking=True) for k, v in hin_dp.items()}
+
+        def step_dp():
+            with torch.no_grad():
+                out_holder["o"] = model(**din_dp)
+
+        for _ in range(3):
+            step_dp()
+        ms_dp = timed(step_dp, args.steps)
+        dp_extra = {"value": args.steps * world / (ms_dp / 1e3), "unit": "samples/s", "ms_per_step": ms_dp / args.steps,
+                    "scaling": "weak", "note": "one independent sample per rank, no data-path collective"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -365,13 +456,19 @@ def main():
     vae = None
     if not args.no_vae and world == 1:
         vae = vae_leg()
+    lib = None
+    if not args.no_library_baseline and world == 1:
+        try:
+            lib = library_baseline_step(dev)
+        except Exception as e:   # a reported baseline must not take the headline down with it
+            lib = {"error": repr(e)[:300]}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         v, cores, sample = cpu_reference_step()
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if args.parallel == "dp" else "strong",   # the --parallel mode the N > 1 runs of this line use
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if args.parallel == "dp" else "strong",   # the --parallel mode the N > 1 runs of this line use (default sp: total work fixed)
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic (seeded N(0,1) latents / T5 embeddings, random-init weights)",
         "config": {"workload": WORKLOAD, "parallelism": mode + str(world), "cuda_graph": bool(args.graph),
                    "l2": "weights 2.2 GB + activations stream through every step (>> 126 MB L2): inputs larger than L2",
@@ -379,8 +476,13 @@ def main():
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_out.numel() * 4,
                 "ms_per_step": ms_e2e / args.steps},
-        "roofline": roof, "cpu_baseline": cpu, "vae": vae,
+        "roofline": roof, "cpu_baseline": cpu, "library_baseline": lib, "vae": vae,
     }
+    if sp_check is not None:
+        line["sp_check"] = sp_check
+        line["config"]["exchange"] = getattr(model, "sp_exchange_kind", "nccl all_to_all_single")
+    if dp_extra is not None:
+        line["dp_replicas"] = dp_extra
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -132,6 +132,7 @@ int osb_attn_short(const osb_attn_short_args* args, void* stream);
  *   mode 1: frame-major stream viewed along T          row = (b*T + t)*S + s -> seq = b*S + s, pos = t  (L == T)
  *   G > 1 : G short sequences packed per tile          tile = seq / G, r = (seq % G)*L + pos   (G*L <= tile_rows, tps == 1)
  *   G == 1: tile = seq*tps + pos / tile_rows, r = pos % tile_rows, tps = ceil(L / tile_rows)                      */
+struct osb_scatter;
 typedef struct osb_tile_map {
   int32_t mode, L, S, T, G, tps, tile_rows, reserved;
 } osb_tile_map;
@@ -180,11 +181,48 @@ typedef struct osb_attn_tiles_args {
   int64_t out_ld;
   float softmax_scale;
   int32_t reserved2;
+  const struct osb_scatter* out_scatter; /* optional: route output rows to peer buffers (sequence parallel), else NULL   */
 } osb_attn_tiles_args;
 
 /* out = softmax(q k^T * scale) v per (sequence, head) over head tiles: persistent CTAs, bulk-copy loads, two
  * query tiles in flight per CTA (open-sora_b200/csrc/attn_tiles_sm100.cu).  Replaces mmdit/math.py:22-36. */
 int osb_attn_tiles(const osb_attn_tiles_args* args, void* stream);
+
+/* ---- sequence-parallel exchange over peer memory (NVLink / NVSwitch) ------------------------- */
+/* The T-shard <-> S-shard transposition around temporal attention (the reference's all_to_all,
+ * opensora/acceleration/communications.py:8-18,57-63) is done by the PRODUCING kernel: it stores every output row
+ * straight into the buffer of the rank that will consume it (peer-mapped symmetric memory created on the Python side,
+ * torch.distributed._symmetric_memory), so there is no pack copy, no collective call and no unpack copy.  osb_scatter
+ * describes the row routing; osb_comm_barrier is the one small kernel that orders producers and consumers across ranks.
+ * NCCL itself stays in Python (torch.distributed) for the entry split / exit all-gather. */
+#define OSB_MAX_PEERS 16
+typedef struct osb_scatter {
+  int32_t mode;   /* 0: none (plain local output).  Rows are viewed as [B, I, J]:
+                     1: J is split over the P ranks: row (b, i, j) goes to rank p = j / (J/P), row
+                        (b*(P*I) + rank*I + i) * (J/P) + j % (J/P) of its buffer   ([B, Tl, S] -> [B, T, S/P]);
+                     2: I is split: row (b, i, j) goes to rank p = i / (I/P), row
+                        (b*(I/P) + i % (I/P)) * (P*J) + rank*J + j of its buffer   ([B, T, Sl] -> [B, T/P, S])       */
+  int32_t P, rank, I, J;
+  int32_t reserved[3];
+  void* peer[OSB_MAX_PEERS];   /* base of the destination buffer on every rank (peer[rank] is the local one)           */
+} osb_scatter;
+
+/* osb_ln_modulate with the output rows routed by `scatter` (row stride C elements on every destination) */
+int osb_ln_modulate_scatter(const void* x, const float* shift, const float* scale, int64_t rows, int C,
+                            int64_t group_rows, const int32_t* mod_index, int64_t mod_stride, float eps,
+                            const osb_scatter* scatter, void* stream);
+
+typedef struct osb_comm_barrier_args {
+  int32_t P, rank;
+  uint32_t* epoch;                   /* local device counter: exchanges completed so far (the kernel increments it)    */
+  uint32_t* flags_local;             /* [P] slots other ranks write into                                               */
+  uint32_t* flags_peer[OSB_MAX_PEERS]; /* the same array on every rank, peer-mapped                                    */
+} osb_comm_barrier_args;
+
+/* One CTA: thread p publishes "my stores of exchange e are done" (st.release.sys) into slot `rank` of rank p's flags,
+ * then waits (ld.acquire.sys) until slot p of the local flags reached e.  Stream order before it = this rank's producer
+ * has completed; after it = every rank's producer has.  Capturable in a CUDA graph (the epoch lives on the device). */
+int osb_comm_barrier(const osb_comm_barrier_args* args, void* stream);
 
 /* ---- causal 3D VAE: implicit-GEMM convolution + its HBM-bound helpers ----------------------------- */
 typedef struct osb_conv3d_args {

@@ -131,6 +131,30 @@ int make_tmap_5d_bf16(CUtensorMap* map, const void* base, const uint64_t dims[5]
   return OSB_OK;
 }
 
+int make_row_scatter(RowScatter* dst, const osb_scatter* src, int64_t rows, const char* who) {
+  *dst = RowScatter();
+  if (src == nullptr || src->mode == 0) return OSB_OK;
+  if (src->mode != 1 && src->mode != 2) { set_error("%s: unknown scatter mode %d", who, src->mode); return OSB_ERR_INVALID; }
+  if (src->P < 1 || src->P > OSB_MAX_PEERS || src->rank < 0 || src->rank >= src->P || src->I <= 0 || src->J <= 0) {
+    set_error("%s: bad scatter (P %d rank %d I %d J %d)", who, src->P, src->rank, src->I, src->J);
+    return OSB_ERR_INVALID;
+  }
+  const int split = src->mode == 1 ? src->J : src->I;
+  if (split % src->P != 0 || rows % ((int64_t)src->I * src->J) != 0 || rows >= (1ll << 31)) {
+    set_error("%s: scatter of [*, %d, %d] rows over %d ranks does not divide (%lld rows)", who, src->I, src->J, src->P, (long long)rows);
+    return OSB_ERR_INVALID;
+  }
+  dst->mode = src->mode; dst->P = src->P; dst->rank = src->rank; dst->I = src->I; dst->J = src->J;
+  for (int p = 0; p < src->P; ++p) {
+    if (src->peer[p] == nullptr || (reinterpret_cast<uintptr_t>(src->peer[p]) & 15)) {
+      set_error("%s: peer buffer %d is null or not 16-byte aligned", who, p);
+      return OSB_ERR_INVALID;
+    }
+    dst->peer[p] = src->peer[p];
+  }
+  return OSB_OK;
+}
+
 int gemm_init();   // gemm_sm100.cu
 int attn_init();   // attn_short_sm100.cu
 int attn_tiles_init();   // attn_tiles_sm100.cu

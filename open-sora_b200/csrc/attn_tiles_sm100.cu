@@ -48,11 +48,30 @@ struct TileAttnParams {
   int32_t nst;              // K/V ring stages
   int32_t resident;         // shared mode and nkb <= nst: key tiles stay across the pairs of one (set, head)
   int32_t off_kv, off_bar;  // shared memory carve-up
+  RowScatter out_sc;        // sequence parallel: output rows go straight to the consuming rank's buffer
 };
+
+#ifdef OSB_TA_TRACE
+// debug build only (tests/ta_trace.py): CTA 0 records (tag, clock64) per role: 0/1 softmax slots, 2 loader, 3 issuer.
+// The event count lives in a register of the tracing lane (a global counter would add an L2 round trip per event).
+__device__ unsigned long long g_ta_trace[4][1024];
+__device__ int g_ta_trace_n[4];
+#define TA_TR_DECL int ta_n_ = 0;
+#define TA_TR(role, tag)                                                                                   \
+  do {                                                                                                     \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && ta_n_ < 512) {                                       \
+      g_ta_trace[role][2 * ta_n_] = (tag); g_ta_trace[role][2 * ta_n_ + 1] = clock64(); ++ta_n_;          \
+      g_ta_trace_n[role] = ta_n_;                                                                          \
+    }                                                                                                      \
+  } while (0)
+#else
+#define TA_TR_DECL
+#define TA_TR(role, tag) do { } while (0)
+#endif
 
 struct PairJob {
   int head;
-  int64_t set[2];
+  int set[2];
   int qt[2];
   bool act[2];
   int keys[2];   // valid key slots of the set (packed tiles: all G * Lk)
@@ -100,40 +119,41 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
 
   pdl_wait();
 
-  // this CTA's contiguous pair range
-  const int64_t pair_lo = (int64_t)blockIdx.x * p.num_pairs / gridDim.x;
-  const int64_t pair_hi = (int64_t)(blockIdx.x + 1) * p.num_pairs / gridDim.x;
+  // this CTA's contiguous pair range (host: num_pairs < 2^31)
+  const int pair_lo = (int)((int64_t)blockIdx.x * p.num_pairs / gridDim.x);
+  const int pair_hi = (int)((int64_t)(blockIdx.x + 1) * p.num_pairs / gridDim.x);
+  const uint32_t ppg = (uint32_t)p.ppg, nH = (uint32_t)p.H;
 
-  auto decode = [&](int64_t pair, PairJob& j) {
+  auto decode = [&](int pair, PairJob& j) {
     if (p.shared_mode) {
-      const int64_t grp = pair / p.ppg;
-      const int jp = (int)(pair - grp * p.ppg);
-      const int64_t set = grp / p.H;
-      j.head = (int)(grp - set * p.H);
-      j.set[0] = j.set[1] = set;
-      j.qt[0] = 2 * jp; j.qt[1] = 2 * jp + 1;
+      const uint32_t grp = (uint32_t)pair / ppg;
+      const uint32_t jp = (uint32_t)pair - grp * ppg;
+      const uint32_t set = grp / nH;
+      j.head = (int)(grp - set * nH);
+      j.set[0] = j.set[1] = (int)set;
+      j.qt[0] = 2 * (int)jp; j.qt[1] = 2 * (int)jp + 1;
       j.act[0] = true; j.act[1] = j.qt[1] < p.qmap.tps;
       int keys = p.Lk;
-      if (p.kv_lens) { const int l = p.kv_lens[set]; keys = l < keys ? (l < 0 ? 0 : l) : keys; }
+      if (p.kv_lens) { const int l = __ldg(p.kv_lens + set); keys = l < keys ? (l < 0 ? 0 : l) : keys; }
       j.keys[0] = j.keys[1] = keys;
-      const int nk = keys > 0 ? (keys + p.BK - 1) / p.BK : 1;
+      const int nk = keys > 0 ? (int)((uint32_t)(keys + p.BK - 1) / (uint32_t)p.BK) : 1;
       j.nkb[0] = j.nkb[1] = nk;
-      const bool same_prev = pair > pair_lo && (pair - 1) / p.ppg == grp;
-      const bool same_next = pair + 1 < pair_hi && (pair + 1) / p.ppg == grp;
+      const bool same_prev = pair > pair_lo && jp > 0;                       // the previous pair belongs to this group
+      const bool same_next = pair + 1 < pair_hi && jp + 1 < ppg;
       j.load = !(p.resident && same_prev);
       j.release = !(p.resident && same_next);
     } else {
-      j.head = (int)(pair / p.ppg);
-      const int64_t ip = pair - (int64_t)j.head * p.ppg;
+      j.head = (int)((uint32_t)pair / ppg);
+      const int ip = pair - j.head * (int)ppg;
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         j.set[s] = 2 * ip + s;
         j.qt[s] = 0;
-        j.act[s] = j.set[s] < p.num_sets;
+        j.act[s] = j.set[s] < (int)p.num_sets;
         int keys = p.qmap.G > 1 ? p.qmap.G * p.Lk : p.Lk;
-        if (p.qmap.G == 1 && p.kv_lens && j.act[s]) { const int l = p.kv_lens[j.set[s]]; keys = l < keys ? (l < 0 ? 0 : l) : keys; }
+        if (p.qmap.G == 1 && p.kv_lens && j.act[s]) { const int l = __ldg(p.kv_lens + j.set[s]); keys = l < keys ? (l < 0 ? 0 : l) : keys; }
         j.keys[s] = keys;
-        j.nkb[s] = keys > 0 ? (keys + p.BK - 1) / p.BK : 1;
+        j.nkb[s] = keys > 0 ? (int)((uint32_t)(keys + p.BK - 1) / (uint32_t)p.BK) : 1;
       }
       j.load = true;
       j.release = true;
@@ -146,9 +166,10 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
     return (n + 15) & ~15;
   };
 
-  // register file: the softmax warpgroups hold a whole 128-column S row per thread; the loader / issuer need almost none
-  if (warp < 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;\n" ::);
-  else asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n" ::);
+  // register file: the softmax warpgroups hold a whole 128-column S row per thread; the loader / issuer need few.
+  // 216 * 256 + 72 * 128 = 168 * 384: exactly what the launch allocated (asking for more blocks forever)
+  if (warp < 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;\n" ::);
+  else asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n" ::);
 
   if (warp < 8) {
     // =========================================== softmax warpgroups ===========================================
@@ -158,12 +179,13 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
     const uint32_t t_o = t_s + 128;
     const float sc = p.scale_log2;
     uint32_t n_s = 0, n_o = 0;
-    for (int64_t pair = pair_lo; pair < pair_hi; ++pair) {
+    TA_TR_DECL
+    for (int pair = pair_lo; pair < pair_hi; ++pair) {
       PairJob j;
       decode(pair, j);
       // this slot's job as scalars (a runtime index into the struct would push it to local memory)
       const bool j_act = slot ? j.act[1] : j.act[0];
-      const int64_t j_set = slot ? j.set[1] : j.set[0];
+      const int j_set = slot ? j.set[1] : j.set[0];
       const int j_qt = slot ? j.qt[1] : j.qt[0];
       const int j_keys = slot ? j.keys[1] : j.keys[0];
       const int nkb = slot ? j.nkb[1] : j.nkb[0];
@@ -176,7 +198,7 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
       if (p.qmap.G > 1) {
         const int g = r / p.qmap.L;
         pos = r - g * p.qmap.L;
-        seq = j_set * p.qmap.G + g;
+        seq = (int64_t)j_set * p.qmap.G + g;
         valid = g < p.qmap.G && seq < p.num_seqs;
         if (valid) { lo = g * p.Lk; hi = lo + p.Lk; }
       } else {
@@ -196,6 +218,7 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
         const int whi = __reduce_max_sync(0xffffffffu, some ? bhi : 0);
         mbar_wait(s_full(slot), n_s & 1); ++n_s;
         tc_fence_after();
+        if ((warp & 3) == 0) TA_TR(slot, 10);
         uint32_t s[4][32];
         bool live[4];
 #pragma unroll
@@ -204,6 +227,7 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
           if (live[c]) tmem_ld_32x32b_x32(t_s + c * 32, s[c]);
         }
         tmem_ld_wait();
+        if ((warp & 3) == 0) TA_TR(slot, 11);
         // ---- block maximum over this row's valid keys ----
         float mb = -INFINITY;
 #pragma unroll
@@ -241,6 +265,7 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
         }
         if (m == -INFINITY) m = mb;
         const float ms = (m == -INFINITY) ? 0.f : m * sc;
+        if ((warp & 3) == 0) TA_TR(slot, 12);
         // ---- P = exp2(S * scale - max), row sum, P (bf16) in place over S ----
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
@@ -278,10 +303,12 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(p_full(slot));
+        if ((warp & 3) == 0) TA_TR(slot, 13);
       }
       // ---- epilogue: last PV done -> normalise, round once, store ----
       mbar_wait(o_full(slot), n_o & 1); ++n_o;
       tc_fence_after();
+      if ((warp & 3) == 0) TA_TR(slot, 14);
       const float inv = l > 0.f ? 1.0f / l : 0.f;
       uint32_t o[Cfg::U * 8];
 #pragma unroll
@@ -294,8 +321,16 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
       }
       tmem_ld_wait();
       tc_fence_before();
+      if ((warp & 3) == 0) TA_TR(slot, 15);
       if (valid) {
-        __nv_bfloat16* orow = p.out + row_of_token(p.qmap, seq, pos) * p.out_ld + (int64_t)j_head * D;
+        int64_t orow_i = row_of_token(p.qmap, seq, pos);
+        __nv_bfloat16* obase = p.out;
+        if (p.out_sc.mode != 0) {
+          int peer;
+          scatter_row(p.out_sc, orow_i, peer, orow_i);
+          obase = static_cast<__nv_bfloat16*>(scatter_base(p.out_sc, peer));
+        }
+        __nv_bfloat16* orow = obase + orow_i * p.out_ld + (int64_t)j_head * D;
 #pragma unroll
         for (int u = 0; u < Cfg::U; ++u) {
           uint4 w;
@@ -310,13 +345,15 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
           *reinterpret_cast<uint4*>(orow + u * 8) = w;
         }
       }
+      if ((warp & 3) == 0) TA_TR(slot, 16);
     }
   } else if (warp == kTALoaderWarp) {
     // =========================================== loader: bulk copies ===========================================
     const bool leader = elect_one();
     uint32_t n_q[2] = {0, 0};
     uint32_t ring = 0;
-    for (int64_t pair = pair_lo; pair < pair_hi; ++pair) {
+    TA_TR_DECL
+    for (int pair = pair_lo; pair < pair_hi; ++pair) {
       PairJob j;
       decode(pair, j);
 #pragma unroll
@@ -324,8 +361,9 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
         if (!j.act[s]) continue;
         mbar_wait(q_empty(s), (n_q[s] & 1) ^ 1);   // the previous job's S MMAs are done with this buffer
         ++n_q[s];
+        TA_TR(2, 20 + s);
         if (leader) {
-          const int64_t qtile = j.set[s] * p.qmap.tps + j.qt[s];
+          const int64_t qtile = (int64_t)j.set[s] * p.qmap.tps + j.qt[s];
           mbar_expect_tx(q_full(s), (uint32_t)p.q_tile_bytes);
           bulk_load_1d(sQ(s), p.q + (int64_t)j.head * p.q_head_stride + qtile * p.q_tile_bytes, (uint32_t)p.q_tile_bytes, q_full(s));
         }
@@ -340,8 +378,9 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
           const int st = (int)(ring % (uint32_t)p.nst);
           mbar_wait(kv_empty(st), ((ring / (uint32_t)p.nst) & 1) ^ 1);
           ++ring;
+          TA_TR(2, 22);
           if (leader) {
-            const int64_t ktile = j.set[s] * p.nkb + kb;
+            const int64_t ktile = (int64_t)j.set[s] * p.nkb + kb;
             const int64_t off = (int64_t)j.head * p.kv_head_stride + ktile * p.kv_tile_bytes;
             mbar_expect_tx(kv_full(st), 2u * (uint32_t)p.kv_tile_bytes);
             bulk_load_1d(sK(st), p.k + off, (uint32_t)p.kv_tile_bytes, kv_full(st));
@@ -359,24 +398,31 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
     const uint32_t idesc_s = make_idesc_bf16_f32(128, (uint32_t)p.BK);
     const uint32_t idesc_om = make_idesc_bf16_f32_bmn(128, NMAIN);
     const uint32_t idesc_ot = make_idesc_bf16_f32_bmn(128, 16);
+    // shared-memory descriptors as (low word with the 16-byte-unit address, constant high word): stepping an operand
+    // is one 32-bit add, and everything stays in uniform registers
+    constexpr uint32_t kHiSw128 = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));   // SBO 1024, version 1, SWIZZLE_128B
+    constexpr uint32_t kHiTailK = (uint32_t)((256u >> 4) | (1u << 14));                  // K-major tail: SBO 256
+    constexpr uint32_t kHiTailMN = (uint32_t)((128u >> 4) | (1u << 14));                 // MN-major tail: SBO 128
+    auto desc = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
+    auto a16 = [](uint32_t addr) { return (addr & 0x3FFFFu) >> 4; };
     const uint32_t q_chunk16 = (uint32_t)(p.qmap.TR * 128) >> 4, k_chunk16 = (uint32_t)(p.BK * 128) >> 4;
+    const uint32_t lbo_tail_k = (128u >> 4) << 16, lbo_tail_mn = (256u >> 4) << 16, lbo_v = (k_chunk16 & 0x3FFFu) << 16;
+    const uint32_t kv_slot16 = (uint32_t)p.kv_slot_bytes >> 4, stage16 = 2 * kv_slot16;
+    const uint32_t q16[2] = {a16(sQ(0)), a16(sQ(1))};
+    const uint32_t kv16 = a16(sK(0));
+    const uint32_t nst = (uint32_t)p.nst;
     uint32_t n_q[2] = {0, 0}, n_p[2] = {0, 0};
     uint32_t ring = 0, set_ring0 = 0;
-    auto t_s = [&](int slot) { return tmem_base + (uint32_t)(slot * 256); };
-    auto t_o = [&](int slot) { return tmem_base + (uint32_t)(slot * 256 + 128); };
+    TA_TR_DECL
 
-    for (int64_t pair = pair_lo; pair < pair_hi; ++pair) {
+    for (int pair = pair_lo; pair < pair_hi; ++pair) {
       PairJob j;
       decode(pair, j);
-      uint32_t base[2];   // ring index of key tile 0 of each slot's set
-      if (p.shared_mode) {
-        if (j.load) { set_ring0 = ring; ring += (uint32_t)j.nkb[0]; }
-        base[0] = base[1] = set_ring0;
-      }
+      if (p.shared_mode && j.load) { set_ring0 = ring; ring += (uint32_t)j.nkb[0]; }
       // split mode: slot s, tile kb sits at ring index r0 + (tiles of both slots issued before it), kb-major
       const uint32_t r0 = ring;
       auto ring_of = [&](int s, int kb) -> uint32_t {
-        if (p.shared_mode) return base[s] + (uint32_t)kb;
+        if (p.shared_mode) return set_ring0 + (uint32_t)kb;
         // tiles of slot 0 with index <= kb (s == 1) or < kb (s == 0), tiles of slot 1 with index < kb
         const int n0 = j.nkb[0] < (s == 1 ? kb + 1 : kb) ? j.nkb[0] : (s == 1 ? kb + 1 : kb);
         const int n1 = !j.act[1] ? 0 : (j.nkb[1] < kb ? j.nkb[1] : kb);
@@ -384,49 +430,56 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
       };
       auto issue_S = [&](int s, int kb) {
         const uint32_t ri = ring_of(s, kb);
-        const int st = (int)(ri % (uint32_t)p.nst);
-        if (kb == 0) { mbar_wait(q_full(s), n_q[s] & 1); ++n_q[s]; }
-        if (p.shared_mode ? (j.load && s == 0) : true) mbar_wait(kv_full(st), (ri / (uint32_t)p.nst) & 1);
+        const uint32_t st = ri % nst;
+        if (kb == 0) { mbar_wait(q_full(s), n_q[s] & 1); ++n_q[s]; TA_TR(3, 30 + s); }
+        if (p.shared_mode ? (j.load && s == 0) : true) { mbar_wait(kv_full((int)st), (ri / nst) & 1); TA_TR(3, 32); }
         tc_fence_after();
-        const uint64_t qd0 = make_sw128_kmajor_desc(sQ(s)), kd0 = make_sw128_kmajor_desc(sK(st));
-        const uint64_t qtd = make_noswz_kmajor_desc(sQ(s) + Cfg::MAIN * p.qmap.TR * 128);
-        const uint64_t ktd = make_noswz_kmajor_desc(sK(st) + Cfg::MAIN * p.BK * 128);
         if (leader) {
+          const uint32_t tS = tmem_base + (uint32_t)(s * 256);
+          const uint32_t qlo = q16[s], klo = kv16 + st * stage16;
           uint32_t acc = 0;
 #pragma unroll
           for (int kc = 0; kc < Cfg::MAIN; ++kc) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              umma_bf16<1>(t_s(s), qd0 + (uint64_t)(kc * q_chunk16 + ks * 2), kd0 + (uint64_t)(kc * k_chunk16 + ks * 2), idesc_s, acc);
+              umma_bf16<1>(tS, desc(qlo + kc * q_chunk16 + ks * 2, kHiSw128), desc(klo + kc * k_chunk16 + ks * 2, kHiSw128), idesc_s, acc);
               acc = 1;
             }
           }
-          if (Cfg::TAIL) umma_bf16<1>(t_s(s), qtd, ktd, idesc_s, acc);
+          if (Cfg::TAIL)
+            umma_bf16<1>(tS, desc((qlo + Cfg::MAIN * q_chunk16) | lbo_tail_k, kHiTailK), desc((klo + Cfg::MAIN * k_chunk16) | lbo_tail_k, kHiTailK), idesc_s, acc);
           umma_commit<1>(s_full(s));
           if (kb == j.nkb[s] - 1) umma_commit<1>(q_empty(s));   // the Q buffer may be refilled for the next job
         }
         __syncwarp();
+        TA_TR(3, 34 + s);
       };
       auto issue_PV = [&](int s, int kb) {
         const uint32_t ri = ring_of(s, kb);
-        const int st = (int)(ri % (uint32_t)p.nst);
+        const uint32_t st = ri % nst;
+        const int steps = ncol_of(j.keys[s], kb) >> 4;
         mbar_wait(p_full(s), n_p[s] & 1); ++n_p[s];
         tc_fence_after();
-        const int steps = ncol_of(j.keys[s], kb) >> 4;
-        const uint64_t vd0 = make_sw128_mnmajor_desc(sV(st), (uint32_t)(p.BK * 128));
-        const uint64_t vt0 = make_noswz_mnmajor_desc(sV(st) + Cfg::MAIN * p.BK * 128);
+        TA_TR(3, 36 + s);
         if (leader) {
-          for (int i = 0; i < steps; ++i) {
-            const uint32_t accu = (kb > 0 || i > 0) ? 1u : 0u;
-            umma_bf16_ts(t_o(s), t_s(s) + (uint32_t)(i * 8), vd0 + (uint64_t)(i * (2048 >> 4)), idesc_om, accu);
-            if (Cfg::TAIL) umma_bf16_ts(t_o(s) + NMAIN, t_s(s) + (uint32_t)(i * 8), vt0 + (uint64_t)(i * (512 >> 4)), idesc_ot, accu);
+          const uint32_t tS = tmem_base + (uint32_t)(s * 256), tO = tS + 128;
+          const uint32_t vlo = (kv16 + st * stage16 + kv_slot16) | lbo_v;
+          const uint32_t vtl = (kv16 + st * stage16 + kv_slot16 + Cfg::MAIN * k_chunk16) | lbo_tail_mn;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (i < steps) {
+              const uint32_t accu = (kb > 0 || i > 0) ? 1u : 0u;
+              umma_bf16_ts(tO, tS + (uint32_t)(i * 8), desc(vlo + i * (2048 >> 4), kHiSw128), idesc_om, accu);
+              if (Cfg::TAIL) umma_bf16_ts(tO + NMAIN, tS + (uint32_t)(i * 8), desc(vtl + i * (512 >> 4), kHiTailMN), idesc_ot, accu);
+            }
           }
           // the stage is free once its last reader is done: slot 1 (or slot 0 alone) in shared mode, the slot itself otherwise
           const bool last_reader = p.shared_mode ? (j.release && (s == 1 || !j.act[1])) : true;
-          if (last_reader) umma_commit<1>(kv_empty(st));
+          if (last_reader) umma_commit<1>(kv_empty((int)st));
           if (kb == j.nkb[s] - 1) umma_commit<1>(o_full(s));
         }
         __syncwarp();
+        TA_TR(3, 38 + s);
       };
       const int nkmax = j.act[1] && j.nkb[1] > j.nkb[0] ? j.nkb[1] : j.nkb[0];
       issue_S(0, 0);
@@ -439,10 +492,7 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
           if (kb + 1 < j.nkb[s]) issue_S(s, kb + 1);
         }
       }
-      if (!p.shared_mode) {
-        ring = r0;
-        ring += (uint32_t)j.nkb[0] + (j.act[1] ? (uint32_t)j.nkb[1] : 0u);
-      }
+      if (!p.shared_mode) ring = r0 + (uint32_t)j.nkb[0] + (j.act[1] ? (uint32_t)j.nkb[1] : 0u);
     }
   }
   __syncwarp();
@@ -487,6 +537,7 @@ static int attn_tiles_launch(TileAttnParams& p, cudaStream_t stream) {
     p.num_pairs = (int64_t)p.ppg * p.H;
     p.resident = 0;
   }
+  if (p.num_pairs >= (1ll << 31) || p.num_sets >= (1ll << 31)) { set_error("osb_attn_tiles: problem too large (%lld query tile pairs)", (long long)p.num_pairs); return OSB_ERR_UNSUPPORTED; }
   const int64_t grid = p.num_pairs < sm_count() ? p.num_pairs : sm_count();
   cudaLaunchAttribute attr[2];
   cudaLaunchConfig_t cfg = launch_config(dim3((unsigned)grid), dim3(kTAThreads), smem, stream, attr);
@@ -496,6 +547,15 @@ static int attn_tiles_launch(TileAttnParams& p, cudaStream_t stream) {
 }
 
 }  // namespace osb
+
+#ifdef OSB_TA_TRACE
+extern "C" int osb_debug_ta_trace(unsigned long long* dst, int* counts) {
+  int zero[4] = {0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(dst, osb::g_ta_trace, sizeof(unsigned long long) * 4 * 1024) != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(counts, osb::g_ta_trace_n, sizeof(int) * 4) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(osb::g_ta_trace_n, zero, sizeof(zero)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" int64_t osb_head_tiles_per_head(const osb_tile_map* m, int64_t rows) {
   if (m == nullptr || m->L <= 0 || m->tile_rows <= 0) return -1;
@@ -508,7 +568,7 @@ extern "C" int osb_attn_tiles(const osb_attn_tiles_args* a, void* stream) {
   using namespace osb;
   if (!initialised()) { set_error("osb_init() has not been called"); return OSB_ERR_NOT_INIT; }
   OSB_REQUIRE(a != nullptr, "osb_attn_tiles: null args");
-  OSB_REQUIRE(a->q_tiles && a->k_tiles && a->v_tiles && a->out, "osb_attn_tiles: null tensor");
+  OSB_REQUIRE(a->q_tiles && a->k_tiles && a->v_tiles && (a->out || a->out_scatter), "osb_attn_tiles: null tensor");
   const int D = a->head_dim;
   OSB_REQUIRE(D == 64 || D == 72 || D == 128, "osb_attn_tiles: head_dim %d not built (64, 72, 128)", D);
   const osb_tile_map& m = a->q_map;
@@ -542,6 +602,11 @@ extern "C" int osb_attn_tiles(const osb_attn_tiles_args* a, void* stream) {
   p.out = static_cast<__nv_bfloat16*>(a->out);
   p.out_ld = a->out_ld;
   p.scale_log2 = a->softmax_scale * 1.4426950408889634f;
+  {
+    const int64_t out_rows = a->num_seqs * m.L;
+    const int rc = make_row_scatter(&p.out_sc, a->out_scatter, out_rows, "osb_attn_tiles");
+    if (rc) return rc;
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (D == 64) return attn_tiles_launch<64>(p, s);
   if (D == 72) return attn_tiles_launch<72>(p, s);

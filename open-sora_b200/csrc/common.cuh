@@ -71,6 +71,10 @@ inline cudaLaunchConfig_t launch_config(dim3 grid, dim3 block, size_t smem, cuda
 int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t ld, uint32_t box_rows, uint32_t box_cols);
 
+struct RowScatter;
+// validates an osb_scatter and copies it into the kernel-parameter form; rows = rows the producer writes
+int make_row_scatter(RowScatter* dst, const osb_scatter* src, int64_t rows, const char* who);
+
 // 5D tiled tensor map over bf16 data: dims/box/element strides innermost first, strides in BYTES for
 // dims 1..4 (multiples of 16), 128-byte swizzle (box[0] must be 64 elements), zero OOB fill.
 int make_tmap_5d_bf16(CUtensorMap* map, const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],
@@ -118,6 +122,16 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
   asm volatile(
       "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
+// relaxed variant: no release fence, i.e. the arrive does not wait for this thread's earlier global stores to become
+// visible.  For hand-offs whose payload is tensor memory (ordered by tcgen05.wait + tcgen05.fence::before_thread_sync),
+// where the release of an epilogue's scattered global stores would otherwise sit on the tensor pipe's critical path.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(bar),
       "r"(cta)
       : "memory");
 }
@@ -388,6 +402,36 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- output row routing to peer buffers (osb_scatter) ----------------------------------------------------------
+struct RowScatter {
+  int32_t mode, P, rank, I, J;
+  void* peer[OSB_MAX_PEERS];
+};
+__device__ __forceinline__ void scatter_row(const RowScatter& sc, int64_t row, int& peer, int64_t& dst_row) {
+  const uint32_t ij = (uint32_t)sc.I * (uint32_t)sc.J;
+  const uint32_t b = (uint32_t)(row / ij);
+  const uint32_t rem = (uint32_t)(row - (int64_t)b * ij);
+  const uint32_t i = rem / (uint32_t)sc.J, j = rem - i * (uint32_t)sc.J;
+  if (sc.mode == 1) {
+    const uint32_t jc = (uint32_t)sc.J / (uint32_t)sc.P;
+    const uint32_t p = j / jc;
+    peer = (int)p;
+    dst_row = ((int64_t)b * sc.P * sc.I + (int64_t)sc.rank * sc.I + i) * jc + (j - p * jc);
+  } else {
+    const uint32_t ic = (uint32_t)sc.I / (uint32_t)sc.P;
+    const uint32_t p = i / ic;
+    peer = (int)p;
+    dst_row = ((int64_t)b * ic + (i - p * ic)) * ((int64_t)sc.P * sc.J) + (int64_t)sc.rank * sc.J + j;
+  }
+}
+// peer[] selected without a runtime index into the parameter struct (which would move it to local memory)
+__device__ __forceinline__ void* scatter_base(const RowScatter& sc, int peer) {
+  void* b = sc.peer[0];
+#pragma unroll
+  for (int k = 1; k < OSB_MAX_PEERS; ++k) b = (peer == k) ? sc.peer[k] : b;
+  return b;
 }
 
 // ---- small math helpers ------------------------------------------------------------------

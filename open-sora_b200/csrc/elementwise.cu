@@ -15,7 +15,8 @@ template <int NCH>  // 16-byte chunks per lane (row has C/8 chunks, lane handles
 __global__ void __launch_bounds__(kLnWarpsPerBlock * 32)
 ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ shift,
                    const float* __restrict__ scale, __nv_bfloat16* __restrict__ y, int64_t rows, int C,
-                   int64_t group_rows, const int32_t* __restrict__ mod_index, int64_t mod_stride, float eps) {
+                   int64_t group_rows, const int32_t* __restrict__ mod_index, int64_t mod_stride, float eps,
+                   const RowScatter rsc) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kLnWarpsPerBlock + (threadIdx.x >> 5);
   pdl_wait();
@@ -70,6 +71,12 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
   const float* sh = shift + g * mod_stride;
   const float* sc = scale + g * mod_stride;
   uint4* yr = reinterpret_cast<uint4*>(y + row * C);
+  if (rsc.mode != 0) {   // sequence parallel: the row goes straight into the buffer of the rank that consumes it (NVLink store)
+    int peer;
+    int64_t drow;
+    scatter_row(rsc, row, peer, drow);
+    yr = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(scatter_base(rsc, peer)) + drow * C);
+  }
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
     const int c = lane + 32 * i;
@@ -96,12 +103,12 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
 
 }  // namespace osb
 
-extern "C" int osb_ln_modulate(const void* x, const float* shift, const float* scale, void* y,
-                               int64_t rows, int C, int64_t group_rows, const int32_t* mod_index,
-                               int64_t mod_stride, float eps, void* stream) {
+static int ln_modulate_launch(const void* x, const float* shift, const float* scale, void* y,
+                              int64_t rows, int C, int64_t group_rows, const int32_t* mod_index,
+                              int64_t mod_stride, float eps, const osb::RowScatter& rsc, void* stream) {
   using namespace osb;
   if (!initialised()) { set_error("osb_init() has not been called"); return OSB_ERR_NOT_INIT; }
-  OSB_REQUIRE(x && y && shift && scale, "osb_ln_modulate: null tensor");
+  OSB_REQUIRE(x && (y || rsc.mode != 0) && shift && scale, "osb_ln_modulate: null tensor");
   OSB_REQUIRE(rows > 0, "osb_ln_modulate: rows must be positive");
   OSB_REQUIRE(C > 0 && C % 8 == 0 && C <= 8192, "osb_ln_modulate: C must be a multiple of 8 and <= 8192 (got %d)", C);
   OSB_REQUIRE(mod_stride % 4 == 0, "osb_ln_modulate: mod_stride must be a multiple of 4");
@@ -119,7 +126,7 @@ extern "C" int osb_ln_modulate(const void* x, const float* shift, const float* s
     cudaLaunchAttribute attr[2];                                                                     \
     cudaLaunchConfig_t cfg = launch_config(dim3(blocks), dim3(kLnWarpsPerBlock * 32), 0, s, attr);   \
     OSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ln_modulate_kernel<N>, xb, shift, scale, yb, rows, C,    \
-                                      group_rows, mod_index, mod_stride, eps));                      \
+                                      group_rows, mod_index, mod_stride, eps, rsc));                 \
     count_launch();                                                                                  \
     return OSB_OK;                                                                                   \
   }
@@ -128,6 +135,80 @@ extern "C" int osb_ln_modulate(const void* x, const float* shift, const float* s
 #undef OSB_LN_CASE
   set_error("osb_ln_modulate: unsupported C %d", C);
   return OSB_ERR_UNSUPPORTED;
+}
+
+extern "C" int osb_ln_modulate(const void* x, const float* shift, const float* scale, void* y,
+                               int64_t rows, int C, int64_t group_rows, const int32_t* mod_index,
+                               int64_t mod_stride, float eps, void* stream) {
+  return ln_modulate_launch(x, shift, scale, y, rows, C, group_rows, mod_index, mod_stride, eps, osb::RowScatter(), stream);
+}
+
+extern "C" int osb_ln_modulate_scatter(const void* x, const float* shift, const float* scale, int64_t rows, int C,
+                                       int64_t group_rows, const int32_t* mod_index, int64_t mod_stride, float eps,
+                                       const osb_scatter* scatter, void* stream) {
+  using namespace osb;
+  OSB_REQUIRE(scatter != nullptr && scatter->mode != 0, "osb_ln_modulate_scatter: no scatter given");
+  RowScatter rsc;
+  const int rc = make_row_scatter(&rsc, scatter, rows, "osb_ln_modulate_scatter");
+  if (rc) return rc;
+  return ln_modulate_launch(x, shift, scale, nullptr, rows, C, group_rows, mod_index, mod_stride, eps, rsc, stream);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// osb_comm_barrier: orders the producers and consumers of a peer-memory exchange across the ranks of one NVSwitch
+// domain.  One CTA; thread p < P: release-store the new epoch into slot `rank` of rank p's flag array, then spin
+// (acquire loads, bounded) until slot p of the local array has reached it.  The epoch counter lives in device memory
+// and is advanced by the kernel itself, so a captured CUDA graph replays correctly.
+// Replaces the synchronisation half of dist.all_to_all (opensora/acceleration/communications.py:8-18).
+// ------------------------------------------------------------------------------------------------------------
+namespace osb {
+struct BarrierParams {
+  int32_t P, rank;
+  uint32_t* epoch;
+  uint32_t* flags_local;
+  uint32_t* flags_peer[OSB_MAX_PEERS];
+};
+__global__ void __launch_bounds__(32) comm_barrier_kernel(const BarrierParams b) {
+  const int p = threadIdx.x;
+  const uint32_t e = *b.epoch + 1u;
+  if (p < b.P) {
+    uint32_t* dst = b.flags_peer[0];
+#pragma unroll
+    for (int k = 1; k < OSB_MAX_PEERS; ++k) dst = (p == k) ? b.flags_peer[k] : dst;
+    // everything this rank's earlier kernels stored to peer memory is ordered before the flag (system scope)
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst + b.rank), "r"(e) : "memory");
+    uint32_t spins = 0;
+    for (;;) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(b.flags_local + p) : "memory");
+      if ((int32_t)(v - e) >= 0) break;
+      if (++spins > (1u << 27)) {
+        printf("osb200: comm barrier timed out (rank %d waiting for rank %d, epoch %u, saw %u)\n", b.rank, p, e, v);
+        __trap();
+      }
+    }
+  }
+  __syncwarp();
+  if (p == 0) *b.epoch = e;
+}
+}  // namespace osb
+
+extern "C" int osb_comm_barrier(const osb_comm_barrier_args* a, void* stream) {
+  using namespace osb;
+  if (!initialised()) { set_error("osb_init() has not been called"); return OSB_ERR_NOT_INIT; }
+  OSB_REQUIRE(a != nullptr && a->P >= 1 && a->P <= OSB_MAX_PEERS && a->rank >= 0 && a->rank < a->P, "osb_comm_barrier: bad ranks");
+  OSB_REQUIRE(a->epoch && a->flags_local, "osb_comm_barrier: null epoch / flags");
+  BarrierParams b = {};
+  b.P = a->P; b.rank = a->rank; b.epoch = a->epoch; b.flags_local = a->flags_local;
+  for (int p = 0; p < a->P; ++p) {
+    OSB_REQUIRE(a->flags_peer[p] != nullptr, "osb_comm_barrier: null peer flag array %d", p);
+    b.flags_peer[p] = a->flags_peer[p];
+  }
+  comm_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(b);
+  OSB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OSB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -302,14 +302,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (kCta == 2) mbar_arrive_cluster(tmem_empty_bar(as), 0);
+        // relaxed: the payload is TMEM (ordered by the fences above); a release here would wait for the previous
+        // tile's scattered global stores to drain while the MMA warp is waiting for this accumulator stage
+        if constexpr (kCta == 2) mbar_arrive_cluster_relaxed(tmem_empty_bar(as), 0);
         else mbar_arrive(tmem_empty_bar(as));
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
       const int64_t col0 = n_blk * BLOCK_N + hh * D;
       if (col0 >= p.N || row >= p.M) continue;
-      const int kidx = (int)(col0 / C);
-      const int head = (int)(col0 - (int64_t)kidx * C) / D;
+      const int kidx = (int)((uint32_t)col0 / (uint32_t)C);
+      const int head = (int)((uint32_t)col0 - (uint32_t)kidx * (uint32_t)C) / D;
       const int kind = kidx % ht.nkinds;
       float x[D];
 #pragma unroll
@@ -328,34 +330,36 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
       // token row -> (sequence position, tile, row in tile)
-      int64_t seq;
-      int pos;
+      // (32-bit arithmetic: the host checks M < 2^31)
+      uint32_t seq, pos;
+      const uint32_t row32 = (uint32_t)row;
       if (ht.map.mode == 0) {
-        seq = row / ht.map.L;
-        pos = (int)(row - seq * ht.map.L);
+        seq = row32 / (uint32_t)ht.map.L;
+        pos = row32 - seq * (uint32_t)ht.map.L;
       } else {
-        const int64_t ts = (int64_t)ht.map.T * ht.map.S;
-        const int64_t b = row / ts;
-        const int64_t rem = row - b * ts;
-        pos = (int)(rem / ht.map.S);
-        seq = b * ht.map.S + (rem - (int64_t)pos * ht.map.S);
+        const uint32_t ts = (uint32_t)ht.map.T * (uint32_t)ht.map.S;
+        const uint32_t b = row32 / ts;
+        const uint32_t rem = row32 - b * ts;
+        pos = rem / (uint32_t)ht.map.S;
+        seq = b * (uint32_t)ht.map.S + (rem - pos * (uint32_t)ht.map.S);
       }
-      int64_t tile_i;
+      uint32_t tile_i;
       int r;
       if (ht.map.G > 1) {
-        tile_i = seq / ht.map.G;
-        r = (int)(seq - tile_i * ht.map.G) * ht.map.L + pos;
+        tile_i = seq / (uint32_t)ht.map.G;
+        r = (int)((seq - tile_i * (uint32_t)ht.map.G) * (uint32_t)ht.map.L + pos);
       } else {
-        const int jt = pos / ht.map.TR;
-        tile_i = seq * ht.map.tps + jt;
-        r = pos - jt * ht.map.TR;
+        const uint32_t jt = pos / (uint32_t)ht.map.TR;
+        tile_i = seq * (uint32_t)ht.map.tps + jt;
+        r = (int)(pos - jt * (uint32_t)ht.map.TR);
       }
       if ((ht.norm_mask >> kind) & 1u) {
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
         for (int i = 0; i < D; i += 4) { s0 += x[i] * x[i]; s1 += x[i + 1] * x[i + 1]; s2 += x[i + 2] * x[i + 2]; s3 += x[i + 3] * x[i + 3]; }
         const float rs = rsqrtf(((s0 + s1) + (s2 + s3)) * (1.0f / D) + ht.eps);
-        const __nv_bfloat16* w = ht.norm_w[kind];
+        // (a runtime index into the parameter struct would move the whole struct to local memory)
+        const __nv_bfloat16* w = kind == 0 ? ht.norm_w[0] : (kind == 1 ? ht.norm_w[1] : (kind == 2 ? ht.norm_w[2] : ht.norm_w[3]));
 #pragma unroll
         for (int u = 0; u < HT::U; ++u) {
           const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w) + u);
@@ -383,7 +387,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
       }
-      uint8_t* dst = ht.base + (int64_t)kidx * ht.kind_stride + (int64_t)head * ht.head_stride + tile_i * ht.tile_bytes;
+      uint8_t* dst = ht.base + (int64_t)kidx * ht.kind_stride + (int64_t)head * ht.head_stride + (int64_t)tile_i * ht.tile_bytes;
       const int chunk_bytes = ht.map.TR * 128;
 #pragma unroll
       for (int u = 0; u < HT::UP; ++u) {
@@ -846,7 +850,7 @@ extern "C" int osb_gemm_head_tiles(const osb_gemm_args* args, const osb_head_til
   const osb_gemm_args& a = *args;
   const osb_head_tiles_args& t = *targs;
   OSB_REQUIRE(a.A && a.W && t.tiles, "osb_gemm_head_tiles: null operand");
-  OSB_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0 && a.K % 8 == 0, "osb_gemm_head_tiles: bad problem (M %lld N %lld K %lld)",
+  OSB_REQUIRE(a.M > 0 && a.M < (1ll << 31) && a.N > 0 && a.N < (1ll << 31) && a.K > 0 && a.K % 8 == 0, "osb_gemm_head_tiles: bad problem (M %lld N %lld K %lld)",
               (long long)a.M, (long long)a.N, (long long)a.K);
   const int D = t.head_dim;
   OSB_REQUIRE(D == 64 || D == 72 || D == 128, "osb_gemm_head_tiles: head_dim %d not built (64, 72, 128)", D);

@@ -162,6 +162,8 @@ class STDiT3(nn.Module):
         self.final_layer = _Final(c.hidden_size, math.prod(self.patch_size), c.out_channels)
         self._cache: dict = {}
         self._sp_group = None
+        self._peer = None
+        self._sp_exchange = "nccl"
         self.register_load_state_dict_post_hook(lambda m, k: m._cache.clear())
 
     # ---- construction helpers ---------------------------------------------------------------
@@ -190,11 +192,39 @@ class STDiT3(nn.Module):
         self._cache = {}
         return super()._apply(fn, *a, **k)
 
-    def enable_sequence_parallel(self, group) -> None:
+    def enable_sequence_parallel(self, group, exchange: str | None = None) -> None:
         """Shard tokens over `group`: T-sharded for spatial / cross / MLP, transposed to
-        S-sharded around each temporal attention with an all-to-all."""
+        S-sharded around each temporal attention.  `exchange`: "peer" = the producing kernels store straight into the
+        consuming rank's buffer over NVLink (opensora/acceleration/peer_exchange.py; default on CUDA), "nccl" = one
+        all_to_all_single per transposition (opensora/acceleration/communications.py; the only choice on gloo / CPU)."""
         self._sp_group = group
         self._cache = {}
+        self._peer = None
+        self._sp_exchange = exchange or os.environ.get("OSB_SP_EXCHANGE", "peer")
+
+    @property
+    def sp_exchange_kind(self) -> str:
+        if self._sp_group is None:
+            return "none"
+        return ("peer stores from the producing kernels (symmetric memory over NVLink) + osb_comm_barrier"
+                if getattr(self, "_peer", None) is not None else "nccl all_to_all_single")
+
+    def _peer_exchange(self, dev):
+        """The PeerExchange of this model (created collectively on first use), or None when the exchange is NCCL's."""
+        if self._sp_group is None or self._sp_exchange != "peer" or dev.type != "cuda" or not self._use_tiles():
+            return None
+        if self._peer is None:
+            try:
+                from opensora.acceleration.peer_exchange import PeerExchange
+
+                self._peer = PeerExchange(self._sp_group, dev)
+            except Exception as e:   # no symmetric memory on this system: the collective path is still correct
+                import warnings
+
+                warnings.warn(f"peer-memory exchange unavailable ({e!r}); using NCCL all_to_all")
+                self._sp_exchange = "nccl"
+                return None
+        return self._peer
 
     # ---- CUDA-graph replay of one step (fixed shapes): removes the ~600 Python-issued launches from the critical
     # path.  Matters when the per-rank work is small (sequence parallel at 8 GPUs is host-bound otherwise). ----------
@@ -385,7 +415,8 @@ class STDiT3(nn.Module):
         ao = torch.empty(R, C, dtype=bf, device=dev)
         hid = torch.empty(R, int(C * self.config.mlp_ratio), dtype=bf, device=dev)
         cos, sin = self._rope(T, dev)
-        ws = dict(xm=xm_buf, ao=ao, hid=hid, cos=cos, sin=sin, kv=kv_all, kv_lens=kv_lens, tiles=use_tiles)
+        ws = dict(xm=xm_buf, ao=ao, hid=hid, cos=cos, sin=sin, kv=kv_all, kv_lens=kv_lens, tiles=use_tiles,
+                  peer=self._peer_exchange(dev) if P > 1 else None)
         if use_tiles:
             Sl = S // P   # temporal attention runs on this rank's S/P columns of every frame
             ws["sp_t"] = self._tiles(osb, ("spatial", B, Tl, S), R, osb.tile_map(0, S), 3, dev)
@@ -439,8 +470,25 @@ class STDiT3(nn.Module):
         kn = a.k_norm.weight if isinstance(a.k_norm, _Norm) else None
         xm_buf, ao, hid, cos, sin, tiles = ws["xm"], ws["ao"], ws["hid"], ws["cos"], ws["sin"], ws["tiles"]
         # 1. self attention (spatial: sequences over S; temporal: sequences over T with RoPE)
-        osb.ln_modulate(xs, m[:, 0], m[:, 1], group_rows=group_rows, mod_index=mod_index, out=xm_buf)
-        if blk.temporal:
+        peer = ws.get("peer") if (blk.temporal and sp is not None) else None
+        if peer is not None:
+            # sequence parallel, peer-memory exchange: LN+modulate stores every row into the xt buffer of the rank that
+            # owns its S-column, the attention epilogue stores every output row into the ao buffer of the rank that owns
+            # its frame; one barrier kernel after each producer.  Rows stay B*T*S/P on both sides.
+            Sl = S // (T // Tl)
+            xt, xt_ptrs = peer.buffer("xt", B * T * Sl, C)
+            ar, ar_ptrs = peer.buffer("ao", B * N, C)
+            osb.ln_modulate(xs, m[:, 0], m[:, 1], group_rows=group_rows, mod_index=mod_index,
+                            scatter=peer.scatter(1, Tl, S, xt_ptrs))
+            peer.barrier()
+            tt = ws["tm_t"]
+            osb.gemm_head_tiles(xt, a.qkv.weight, a.qkv.bias, tt, nkinds=3, norm_w=(qn, kn, None), rope=(cos, sin),
+                                rope_kinds=0b011)
+            osb.attn_tiles(tt, tt, None, Lk=T, num_seqs=B * Sl, out_scatter=peer.scatter(2, T, Sl, ar_ptrs), out_ld=C)
+            peer.barrier()
+            ao = ar
+        elif blk.temporal:
+            osb.ln_modulate(xs, m[:, 0], m[:, 1], group_rows=group_rows, mod_index=mod_index, out=xm_buf)
             if sp is not None:
                 # T-sharded -> S-sharded transposition (all-to-all over NVLink), attention over the full T
                 # for this rank's S/P columns, and back.  Rows stay B*T*S/P on both sides.
@@ -466,10 +514,12 @@ class STDiT3(nn.Module):
             if sp is not None:
                 ao = all_to_all(ao_t.view(B, T, Sl, C), sp, scatter_dim=1, gather_dim=2).view(B * N, C)
         elif tiles:
+            osb.ln_modulate(xs, m[:, 0], m[:, 1], group_rows=group_rows, mod_index=mod_index, out=xm_buf)
             st = ws["sp_t"]
             osb.gemm_head_tiles(xm_buf, a.qkv.weight, a.qkv.bias, st, nkinds=3, norm_w=(qn, kn, None))
             osb.attn_tiles(st, st, ao, Lk=S, num_seqs=B * Tl)
         else:
+            osb.ln_modulate(xs, m[:, 0], m[:, 1], group_rows=group_rows, mod_index=mod_index, out=xm_buf)
             qkv = ws["qkv"]
             osb.gemm(xm_buf, a.qkv.weight, a.qkv.bias, out=qkv)
             strides = (N, S, 1)

@@ -30,6 +30,8 @@ EXPORTS = (
     "osb_head_tiles_per_head",
     "osb_attn_tiles",
     "osb_tmap_cache_stats",
+    "osb_ln_modulate_scatter",
+    "osb_comm_barrier",
 )
 
 EPI_BIAS, EPI_BIAS_GELU_TANH, EPI_BIAS_GATE_RES = 0, 1, 2
@@ -73,6 +75,11 @@ def _load() -> C.CDLL:
     lib.osb_head_tiles_per_head.restype = C.c_int64
     lib.osb_tmap_cache_stats.argtypes = [C.c_void_p, C.c_void_p]
     lib.osb_tmap_cache_stats.restype = None
+    lib.osb_ln_modulate_scatter.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_float,
+        C.c_void_p, C.c_void_p,
+    ]
+    lib.osb_comm_barrier.argtypes = [C.c_void_p, C.c_void_p]
     return lib
 
 
@@ -237,8 +244,43 @@ def require_cuda_bf16(t, what: str) -> None:
                        "there is no CPU / eager fallback")
 
 
-def ln_modulate(x, shift, scale, *, group_rows: int, mod_index=None, eps: float = 1e-6, out=None):
-    """y = LN(x) * (1 + scale[g]) + shift[g];  x bf16 [rows, C]; shift/scale fp32 [G, C] views."""
+MAX_PEERS = 16
+
+
+class Scatter(C.Structure):
+    """include/osb200.h `osb_scatter`: output rows viewed as [B, I, J] are routed to peer buffers (sequence parallel)."""
+    _fields_ = [("mode", C.c_int32), ("P", C.c_int32), ("rank", C.c_int32), ("I", C.c_int32), ("J", C.c_int32),
+                ("reserved", C.c_int32 * 3), ("peer", C.c_void_p * MAX_PEERS)]
+
+
+class CommBarrierArgs(C.Structure):
+    _fields_ = [("P", C.c_int32), ("rank", C.c_int32), ("epoch", C.c_void_p), ("flags_local", C.c_void_p),
+                ("flags_peer", C.c_void_p * MAX_PEERS)]
+
+
+def make_scatter(mode: int, P: int, rank: int, I: int, J: int, peer_ptrs) -> Scatter:
+    sc = Scatter()
+    sc.mode, sc.P, sc.rank, sc.I, sc.J = mode, P, rank, I, J
+    for i, ptr in enumerate(peer_ptrs):
+        sc.peer[i] = int(ptr)
+    return sc
+
+
+def comm_barrier(P: int, rank: int, epoch, flags_local_ptr: int, flags_peer_ptrs) -> None:
+    """Cross-rank ordering point of a peer-memory exchange (osb_comm_barrier): enqueued on the current stream."""
+    import torch
+
+    _need(epoch, torch.int32, "epoch")
+    a = CommBarrierArgs()
+    a.P, a.rank, a.epoch, a.flags_local = P, rank, epoch.data_ptr(), int(flags_local_ptr)
+    for i, ptr in enumerate(flags_peer_ptrs):
+        a.flags_peer[i] = int(ptr)
+    _check(_lib.osb_comm_barrier(C.byref(a), _stream()), "osb_comm_barrier")
+
+
+def ln_modulate(x, shift, scale, *, group_rows: int, mod_index=None, eps: float = 1e-6, out=None, scatter: Scatter | None = None):
+    """y = LN(x) * (1 + scale[g]) + shift[g];  x bf16 [rows, C]; shift/scale fp32 [G, C] views.  With `scatter` the rows
+    are stored straight into peer buffers (osb_ln_modulate_scatter) and nothing is returned."""
     import torch
 
     _need(x, torch.bfloat16, "x"); _need(shift, torch.float32, "shift"); _need(scale, torch.float32, "scale")
@@ -246,6 +288,11 @@ def ln_modulate(x, shift, scale, *, group_rows: int, mod_index=None, eps: float 
     assert x.dim() == 2 and x.is_contiguous()
     assert shift.dim() == 2 and scale.dim() == 2 and shift.stride(0) == scale.stride(0)
     rows, Cdim = x.shape
+    if scatter is not None:
+        with _Timed("ln_modulate", 4.0 * rows * Cdim):
+            _check(_lib.osb_ln_modulate_scatter(_ptr(x), _ptr(shift), _ptr(scale), rows, Cdim, group_rows, _ptr(mod_index),
+                                                shift.stride(0), eps, C.byref(scatter), _stream()), "osb_ln_modulate_scatter")
+        return None
     if out is None:
         out = torch.empty_like(x)
     with _Timed("ln_modulate", 4.0 * rows * Cdim):  # algorithmic bytes: read x + write y (bf16)
@@ -349,7 +396,7 @@ class AttnTilesArgs(C.Structure):
         ("kv_tile_rows", C.c_int32), ("kv_tiles_per_set", C.c_int32), ("Lk", C.c_int32),
         ("num_heads", C.c_int32), ("head_dim", C.c_int32), ("reserved", C.c_int32),
         ("num_seqs", C.c_int64), ("kv_lens", C.c_void_p), ("out", C.c_void_p), ("out_ld", C.c_int64),
-        ("softmax_scale", C.c_float), ("reserved2", C.c_int32),
+        ("softmax_scale", C.c_float), ("reserved2", C.c_int32), ("out_scatter", C.c_void_p),
     ]
 
 
@@ -429,12 +476,14 @@ def gemm_head_tiles(a, w, bias, tiles: HeadTiles, *, nkinds: int, norm_w=(), rop
 
 
 def attn_tiles(q: HeadTiles, kv: HeadTiles, out, *, q_kind: int = 0, k_kind: int = 1, v_kind: int = 2, Lk: int,
-               num_seqs: int, kv_lens=None, softmax_scale: float | None = None):
+               num_seqs: int, kv_lens=None, softmax_scale: float | None = None, out_scatter: Scatter | None = None,
+               out_ld: int | None = None):
     """out = softmax(q k^T * scale) v per (sequence, head) over head tiles (osb_attn_tiles).  Self-attention: q and kv
     are the same buffer (kinds 0, 1, 2); cross-attention: kv holds the text keys / values (`keys_only` map)."""
     import torch
 
     _need(out, torch.bfloat16, "out"); _need(kv_lens, torch.int32, "kv_lens")
+    assert (out is None) != (out_scatter is None), "exactly one of out / out_scatter"
     a = AttnTilesArgs()
     a.q_tiles, a.k_tiles, a.v_tiles = q.kind_ptr(q_kind), kv.kind_ptr(k_kind), kv.kind_ptr(v_kind)
     a.q_head_stride, a.kv_head_stride, a.q_map = q.head_stride, kv.head_stride, q.map
@@ -443,7 +492,11 @@ def attn_tiles(q: HeadTiles, kv: HeadTiles, out, *, q_kind: int = 0, k_kind: int
     a.Lk, a.num_heads, a.head_dim = Lk, q.heads, q.head_dim
     a.num_seqs = num_seqs
     a.kv_lens = kv_lens.data_ptr() if kv_lens is not None else None
-    a.out, a.out_ld = out.data_ptr(), out.stride(0)
+    if out_scatter is not None:   # rows go to peer buffers (row stride out_ld elements on every destination)
+        a.out, a.out_ld = None, int(out_ld)
+        a.out_scatter = C.addressof(out_scatter)
+    else:
+        a.out, a.out_ld = out.data_ptr(), out.stride(0)
     a.softmax_scale = softmax_scale if softmax_scale is not None else q.head_dim ** -0.5
     with _Timed("attn_tiles", 4.0 * num_seqs * q.map.L * Lk * q.heads * q.head_dim):
         _check(_lib.osb_attn_tiles(C.byref(a), _stream()), "osb_attn_tiles")

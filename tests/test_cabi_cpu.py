@@ -119,3 +119,59 @@ def test_product_tree_knows_nothing_of_the_test_double_or_the_oracle():
                 if "fake_osb200" in txt or "import oracle" in txt or "from oracle" in txt:
                     offenders.append(os.path.join(d, f))
     assert not offenders, offenders
+
+
+def test_head_tile_and_exchange_struct_layouts_match_header():
+    """ctypes mirrors of the round-2 structs (head tiles, peer-memory exchange) against a gcc-compiled probe: sizes and the
+    offsets of the last / alignment-sensitive fields."""
+    import subprocess
+    import tempfile
+
+    import osb200
+
+    fields = [
+        ("sizeof(osb_tile_map)", ctypes.sizeof(osb200.TileMap)),
+        ("sizeof(osb_head_tiles_args)", ctypes.sizeof(osb200.HeadTilesArgs)),
+        ("offsetof(osb_head_tiles_args, norm_w)", osb200.HeadTilesArgs.norm_w.offset),
+        ("offsetof(osb_head_tiles_args, rope_sin)", osb200.HeadTilesArgs.rope_sin.offset),
+        ("sizeof(osb_attn_tiles_args)", ctypes.sizeof(osb200.AttnTilesArgs)),
+        ("offsetof(osb_attn_tiles_args, num_seqs)", osb200.AttnTilesArgs.num_seqs.offset),
+        ("offsetof(osb_attn_tiles_args, out_scatter)", osb200.AttnTilesArgs.out_scatter.offset),
+        ("sizeof(osb_scatter)", ctypes.sizeof(osb200.Scatter)),
+        ("offsetof(osb_scatter, peer)", osb200.Scatter.peer.offset),
+        ("sizeof(osb_comm_barrier_args)", ctypes.sizeof(osb200.CommBarrierArgs)),
+        ("offsetof(osb_comm_barrier_args, flags_peer)", osb200.CommBarrierArgs.flags_peer.offset),
+        ("OSB_MAX_PEERS", osb200.MAX_PEERS),
+    ]
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "probe.c")
+        with open(src, "w") as f:
+            f.write('#include <stdio.h>\n#include <stddef.h>\n#include "osb200.h"\nint main(){\n')
+            for expr, _ in fields:
+                f.write(f'printf("%zu\\n", (size_t)({expr}));\n')
+            f.write("return 0;}\n")
+        exe = os.path.join(d, "probe")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        got = [int(v) for v in subprocess.check_output([exe]).split()]
+    for (expr, mine), theirs in zip(fields, got):
+        assert mine == theirs, (expr, mine, theirs)
+
+
+def test_tile_map_arithmetic():
+    """tile_map() (host) against the documented rules of include/osb200.h: packing, ragged tiles, balanced key tiles."""
+    import osb200
+
+    def km(*a, **k):
+        return osb200.tile_map(*a, **k).key()
+
+    assert km(0, 256) == (0, 256, 0, 0, 1, 2, 128)                  # STDiT3 spatial: 2 tiles per sequence
+    assert km(1, 64, 256, 64) == (1, 64, 256, 64, 2, 1, 128)        # temporal: 2 sequences per tile
+    assert km(0, 300, keys_only=True) == (0, 300, 0, 0, 1, 3, 112)  # T5 keys: 3 balanced tiles
+    assert km(0, 16384, pack=False) == (0, 16384, 0, 0, 1, 128, 128)
+    assert km(0, 64, pack=False) == (0, 64, 0, 0, 1, 1, 64)         # cross-attention queries are never packed
+    assert km(1, 17, 100, 17) == (1, 17, 100, 17, 7, 1, 128)        # 7 x 17 = 119 rows -> 128
+    assert km(1, 100, 6, 100) == (1, 100, 6, 100, 1, 1, 112)
+    m = osb200.tile_map(0, 200)
+    assert osb200._lib.osb_head_tiles_per_head(ctypes.byref(m), 5 * 200) == 10
+    m = osb200.tile_map(1, 16, 12, 16)
+    assert osb200._lib.osb_head_tiles_per_head(ctypes.byref(m), 2 * 16 * 12) == 3   # 24 sequences, 8 per tile

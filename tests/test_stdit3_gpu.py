@@ -64,3 +64,76 @@ def test_xl_parity_reduced_latent():
     rn = rel_l2(noise, ref)
     print(f"[parity] oracle-in-bf16 noise floor rel_l2={rn:.3e}")
     assert r < 3e-2 and r < max(1.5 * rn, 6e-3)
+
+
+def _block_trace(prod, oracle, inp):
+    """Residual stream after every block of the product (bf16) and of the fp32 oracle: SURVEY.md 8d "Parity report"
+    (first-divergence localisation)."""
+    ref_x, got_x = [], []
+    hooks = [b.register_forward_hook(lambda m, a, out: ref_x.append(out.detach().float()))
+             for pair in zip(oracle.spatial_blocks, oracle.temporal_blocks) for b in pair]
+    orig = prod._block
+
+    def traced(osb, blk, bi, xs, *a, **k):
+        r = orig(osb, blk, bi, xs, *a, **k)
+        got_x.append(xs.detach().float().clone())
+        return r
+
+    prod._block = traced
+    try:
+        with torch.no_grad():
+            ref = oracle(**inp)
+            out = prod(**inp)
+    finally:
+        prod._block = orig
+        for h in hooks:
+            h.remove()
+    per_block = [rel_l2(g.view_as(r), r) for g, r in zip(got_x, ref_x)]
+    return out, ref, per_block
+
+
+def test_xl_parity_at_the_benchmark_shape():
+    """STDiT3-XL/2, full depth, on the BASELINE.json latent 1x4x64x32x32 (T = 64, S = 256, 16 384 tokens: two query tiles
+    per spatial sequence, two temporal sequences packed per tile, 3 text key tiles) against the fp32 oracle on the same GPU,
+    with the per-block error trace.  Bars: final output within 1.5x of the oracle's own bf16 noise floor (measured here) and
+    below 3e-2; the residual stream may not jump by more than 3x between consecutive blocks (a broken block would)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import stdit3_oracle as O
+    from tests.smoke_impl import build_pair
+
+    prod, oracle, cfg = build_pair("xl")
+    inp = O.synthetic_inputs(cfg, B=1, T=64, H=32, W=32, lens=[260])
+    inp = {k: (v.to(torch.bfloat16).float() if v.is_floating_point() else v).cuda() for k, v in inp.items()}
+    oracle = oracle.cuda()
+    out, ref, per_block = _block_trace(prod, oracle, inp)
+    with torch.no_grad():
+        noise = oracle.to(torch.bfloat16)(**inp)
+    r, _ = report("STDiT3-XL/2 64x32x32 (benchmark shape)", out, ref)
+    rn = rel_l2(noise, ref)
+    print(f"[parity] oracle-in-bf16 noise floor rel_l2={rn:.3e}")
+    print("[parity] residual stream rel_l2 after block k: " + " ".join(f"{k}:{e:.1e}" for k, e in enumerate(per_block)))
+    assert len(per_block) == 2 * cfg.depth
+    assert torch.isfinite(out).all()
+    assert per_block[0] < 5e-3, per_block[0]
+    for k in range(1, len(per_block)):
+        assert per_block[k] < 3.0 * per_block[k - 1] + 2e-3, (k, per_block[k - 1], per_block[k])
+    assert r < 3e-2 and r < max(1.5 * rn, 6e-3), (r, rn)
+
+
+def test_register_path_matches_tile_path(monkeypatch):
+    """The same model through the register-path attention (OSB_ATTN_TILES=0: token-layout q/k/v + osb_attn_short) and through
+    head tiles: both are checked against the oracle elsewhere, here against each other."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import stdit3_oracle as O
+    from tests.smoke_impl import build_pair
+
+    prod, _, cfg = build_pair("xs")
+    inp = O.synthetic_inputs(cfg, B=2, T=8, H=16, W=16, lens=[300, 21])
+    inp = {k: (v.to(torch.bfloat16).float() if v.is_floating_point() else v).cuda() for k, v in inp.items()}
+    with torch.no_grad():
+        a = prod(**inp)
+        monkeypatch.setenv("OSB_ATTN_TILES", "0")
+        b = prod(**inp)
+    assert rel_l2(a, b) < 1e-2
