@@ -26,9 +26,15 @@ group_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t positions, int C
   const int64_t p0 = (int64_t)blockIdx.x * kStatsPositionsPerBlock;
   const int64_t p1 = p0 + kStatsPositionsPerBlock < positions ? p0 + kStatsPositionsPerBlock : positions;
   const uint4* base = reinterpret_cast<const uint4*>(x + (int64_t)n * positions * C);
-  float s[8], q[8];
+  float s[8], q[8], k[8];
+  // sums are taken relative to a per-(n, group) shift K = the group's first element: E[(x-K)^2] - E[x-K]^2 cancels on
+  // the scale of |mean - K| ~ std instead of |mean| (a group with |mean| >> std would lose its variance in fp32)
+  const int v0 = threadIdx.x % vecs;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
+  for (int e = 0; e < 8; ++e) {
+    s[e] = 0.f; q[e] = 0.f;
+    k[e] = __bfloat162float(x[(int64_t)n * positions * C + ((v0 * 8 + e) / cg) * cg]);
+  }
   for (int64_t i = p0 * vecs + threadIdx.x; i < p1 * vecs; i += kStatsThreads) {
     uint4 t;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -37,8 +43,9 @@ group_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t positions, int C
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float2 f = unpack_bf16x2(tw[e]);
-      s[2 * e] += f.x; q[2 * e] += f.x * f.x;
-      s[2 * e + 1] += f.y; q[2 * e + 1] += f.y * f.y;
+      const float d0 = f.x - k[2 * e], d1 = f.y - k[2 * e + 1];
+      s[2 * e] += d0; q[2 * e] += d0 * d0;
+      s[2 * e + 1] += d1; q[2 * e + 1] += d1 * d1;
     }
   }
 #pragma unroll
@@ -59,7 +66,7 @@ group_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t positions, int C
 // one block per (n, group): fixed-order strided sums + tree in fp64
 __global__ void __launch_bounds__(256)
 group_stats_finalize_kernel(const float* __restrict__ partial, float* __restrict__ mean_rstd, int64_t chunks, int ng,
-                            double count, float eps) {
+                            double count, float eps, const __nv_bfloat16* __restrict__ x, int64_t positions, int C, int groups) {
   __shared__ double rs[256], rq[256];
   const int i = blockIdx.x;  // n * groups + g
   double s = 0.0, q = 0.0;
@@ -75,9 +82,12 @@ group_stats_finalize_kernel(const float* __restrict__ partial, float* __restrict
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    const double mean = rs[0] / count;
-    double var = rq[0] / count - mean * mean;
+    const int n = i / groups, g = i - n * groups;
+    const double shift = (double)__bfloat162float(x[(int64_t)n * positions * C + g * (C / groups)]);   // the kernel's K
+    const double dm = rs[0] / count;
+    double var = rq[0] / count - dm * dm;
     if (var < 0.0) var = 0.0;
+    const double mean = shift + dm;
     mean_rstd[2 * i] = (float)mean;
     mean_rstd[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
   }
@@ -170,7 +180,8 @@ extern "C" int osb_group_stats(const void* x, int64_t nb, int64_t positions, int
   group_stats_kernel<<<dim3((unsigned)chunks, (unsigned)nb), kStatsThreads, 0, s>>>(
       static_cast<const __nv_bfloat16*>(x), positions, C, groups, static_cast<float*>(workspace));
   group_stats_finalize_kernel<<<ng, 256, 0, s>>>(static_cast<const float*>(workspace), mean_rstd, chunks, ng,
-                                                 (double)positions * (C / groups), eps);
+                                                 (double)positions * (C / groups), eps,
+                                                 static_cast<const __nv_bfloat16*>(x), positions, C, groups);
   OSB_CHECK_CUDA(cudaGetLastError());
   count_launch(2);
   return OSB_OK;

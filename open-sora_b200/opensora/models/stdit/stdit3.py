@@ -171,7 +171,15 @@ class STDiT3(nn.Module):
     def from_pretrained(cls, path: str | None = None, **kwargs):
         """`STDiT3.from_pretrained(weight_path, **model_kwargs)` (gradio/app.py:124): local directory or
         file holding `model.safetensors` / a torch state dict.  No hub download (no network)."""
-        model = cls(STDiT3Config(**{k: v for k, v in kwargs.items() if k in STDiT3Config.__dataclass_fields__}))
+        cfg_kw = {}
+        if path and os.path.isdir(path) and os.path.exists(os.path.join(path, "config.json")):
+            import json
+
+            with open(os.path.join(path, "config.json")) as fh:   # the checkpoint's own architecture, overridden by kwargs
+                cfg_kw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in json.load(fh).items()
+                          if k in STDiT3Config.__dataclass_fields__}
+        cfg_kw.update({k: v for k, v in kwargs.items() if k in STDiT3Config.__dataclass_fields__})
+        model = cls(STDiT3Config(**cfg_kw))
         if path:
             f = path
             if os.path.isdir(path):
@@ -185,7 +193,13 @@ class STDiT3(nn.Module):
                 sd = load_file(f)
             else:
                 sd = torch.load(f, map_location="cpu")
-            model.load_state_dict(sd, strict=False)
+            res = model.load_state_dict(sd, strict=False)
+            # y_embedding is a buffer older checkpoints may lack; anything else missing or unexpected means the file does
+            # not belong to this architecture and the model would silently keep random weights
+            missing = [k for k in res.missing_keys if k != "y_embedder.y_embedding"]
+            if missing or res.unexpected_keys:
+                raise RuntimeError(f"{f}: state dict does not match STDiT3 ({len(missing)} missing, e.g. {missing[:3]}; "
+                                   f"{len(res.unexpected_keys)} unexpected, e.g. {list(res.unexpected_keys)[:3]})")
         return model
 
     def _apply(self, fn, *a, **k):  # .to()/.cuda()/.bfloat16() invalidate the packed-weight cache
@@ -353,16 +367,20 @@ class STDiT3(nn.Module):
         pos = self._pos_embed(H, W, scale, round(S**0.5), dev)
 
         # ---- conditioning vectors (tiny: M = B rows) --------------------------------------------
-        def emb(e, v):
-            f = _timestep_embedding(v.to(dev).float().reshape(-1), e.frequency_embedding_size).to(bf)
+        def emb(e, v, cast_input):
+            # upstream casts `timestep` to the model dtype BEFORE the sinusoidal embedding (x, timestep, y = .to(dtype);
+            # oracle/stdit3_oracle.py forward): 537 becomes 536 in bf16.  fps is embedded at full precision.
+            v = v.to(dev)
+            v = v.to(bf).float() if cast_input else v.float()
+            f = _timestep_embedding(v.reshape(-1), e.frequency_embedding_size).to(bf)
             h = osb.gemm(f, e.mlp[0].weight, e.mlp[0].bias)
             return osb.gemm(torch.nn.functional.silu(h), e.mlp[2].weight, e.mlp[2].bias)
 
-        fps_e = emb(self.fps_embedder, fps)
+        fps_e = emb(self.fps_embedder, fps, False)
         if fps_e.shape[0] != B:
             fps_e = fps_e.repeat(B // fps_e.shape[0], 1)
         ts = [timestep] + ([torch.zeros_like(timestep)] if x_mask is not None else [])
-        t_all = torch.cat([emb(self.t_embedder, t_) + fps_e for t_ in ts], 0)            # [B or 2B, C]
+        t_all = torch.cat([emb(self.t_embedder, t_, True) + fps_e for t_ in ts], 0)            # [B or 2B, C]
         t_mlp = osb.gemm(torch.nn.functional.silu(t_all), self.t_block[1].weight, self.t_block[1].bias)  # [., 6C]
         nb = 2 * self.depth
         # modulation for every block at once: [B', nb, 6, C] fp32  (table + t), App. A "Modulation"

@@ -54,3 +54,33 @@ def test_single_rank_is_identity():
     x = torch.randn(2, 3, 4)
     assert all_to_all(x, None) is x
     assert gather_forward_split_backward(x, None, 1) is x
+
+
+@pytest.mark.parametrize("P,B,T,S", [(2, 2, 4, 6), (4, 1, 8, 12), (8, 1, 64, 256)])
+def test_peer_scatter_routing_equals_all_to_all(P, B, T, S):
+    """The row routing the kernels use for the peer-memory exchange (osb_scatter) reproduces the reference's all_to_all
+    semantics (communications.py:8-18): simulated for P ranks in one process, both directions."""
+    from opensora.acceleration.peer_exchange import scatter_dest
+
+    C, Tl, Sl = 3, T // P, S // P
+    full = torch.arange(B * T * S * C, dtype=torch.float32).view(B, T, S, C)
+    # T-sharded -> S-sharded (mode 1): producers hold [B, Tl, S], consumers must end up with full[:, :, p*Sl:(p+1)*Sl]
+    recv = [torch.full((B * T * Sl, C), -1.0) for _ in range(P)]
+    for r in range(P):
+        src = full[:, r * Tl:(r + 1) * Tl].reshape(B * Tl * S, C)
+        for row in range(src.shape[0]):
+            p, d = scatter_dest(1, P, r, Tl, S, row)
+            recv[p][d] = src[row]
+    for p in range(P):
+        assert torch.equal(recv[p].view(B, T, Sl, C), full[:, :, p * Sl:(p + 1) * Sl])
+    # S-sharded -> T-sharded (mode 2): producers hold [B, T, Sl], consumers must end up with full[:, p*Tl:(p+1)*Tl]
+    back = [torch.full((B * Tl * S, C), -1.0) for _ in range(P)]
+    for r in range(P):
+        src = full[:, :, r * Sl:(r + 1) * Sl].reshape(B * T * Sl, C)
+        for row in range(0, src.shape[0], 1 if src.shape[0] < 4096 else 7):   # sampled at the large shape
+            p, d = scatter_dest(2, P, r, T, Sl, row)
+            back[p][d] = src[row]
+    for p in range(P):
+        want = full[:, p * Tl:(p + 1) * Tl].reshape(B * Tl * S, C)
+        hit = back[p][:, 0] >= 0
+        assert hit.any() and torch.equal(back[p][hit], want[hit])

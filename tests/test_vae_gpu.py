@@ -48,6 +48,21 @@ def test_group_stats(osb, C, groups, shape):
     torch.testing.assert_close(st[..., 1], torch.rsqrt(var + 1e-6), rtol=1e-4, atol=1e-5)
 
 
+def test_group_stats_large_mean_small_std(osb):
+    """|mean| >> std (mean 60, std 0.25 after bf16 rounding): E[x^2] - mean^2 in fp32 partials would lose the variance; the
+    kernel's shifted sums must not (torch.nn.GroupNorm uses Welford)."""
+    nb, T, H, W, C, groups = 1, 4, 24, 24, 64, 8
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = (60.0 + 0.25 * torch.randn(nb, T, H, W, C, generator=g, device="cuda")).to(torch.bfloat16)
+    st = osb.group_stats(x, groups, 1e-6)
+    xf = x.double().view(nb, T * H * W, groups, C // groups)
+    mean = xf.mean(dim=(1, 3))
+    var = xf.var(dim=(1, 3), unbiased=False)
+    assert float(var.min()) > 0.01
+    torch.testing.assert_close(st[..., 0].double(), mean, rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(st[..., 1].double(), torch.rsqrt(var + 1e-6), rtol=2e-3, atol=0)
+
+
 @pytest.mark.parametrize("up", [(1, 1, 1), (2, 2, 2), (1, 2, 2)])
 def test_vae_prep(osb, up):
     from oracle import vae_oracle as V
