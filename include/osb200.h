@@ -148,7 +148,9 @@ typedef struct osb_head_tiles_args {
   int32_t nkinds;           /* column group kidx is of kind kidx % nkinds                                            */
   uint32_t norm_mask;       /* bit k: kind k gets per-head RMSNorm with norm_w[k]        (layers.py:102-135)         */
   uint32_t rope_mask;       /* bit k: kind k gets interleaved-pair RoPE by position      (math.py:60-65)             */
-  int32_t reserved;
+  int32_t reserved;         /* bit 0: force the general per-row-store epilogue (default: when a CTA's rows coincide with
+                               one tile - contiguous sequences of whole 128-row tiles, or the temporal view loaded through
+                               a strided TMA box - the tile image is staged in shared memory and bulk-stored)           */
   const void* norm_w[4];    /* bf16 [head_dim] per kind or NULL                                                      */
   float norm_eps;
   int32_t reserved2;

@@ -10,6 +10,8 @@
 // Replaces every nn.Linear on the denoiser block path of the reference
 // (opensora/models/mmdit/layers.py:209-214,247-252,277-281,314-334,401) and the fused epilogues
 // replace the separate bias / GELU(tanh) / gate*x+residual elementwise kernels.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tiles.cuh"
 
@@ -53,6 +55,15 @@ struct HeadTileParams {
   float eps;
   const float* cos;
   const float* sin;
+  // aligned fast path: every CTA's 128 accumulator rows ARE one head tile (row r of the CTA = row r of the tile), so the
+  // epilogue builds the tile image in shared memory and writes it with one bulk store per head.
+  //   1: contiguous sequences with tile_rows == 128 and L % 128 == 0 (tile = CTA's row block);
+  //   2: temporal view: the A operand is loaded through a strided TMA view [k][t][s][b] whose box is (64, T, G):
+  //      the M-tile of (batch b, sequence group sg) holds rows g*T + t - exactly the packed temporal attention tile.
+  int32_t fast;
+  int32_t a_rows;         // accumulator rows that carry data (128, or G*T in mode 2)
+  int32_t tiles_total;    // head tiles per head
+  int32_t groups_per_batch;   // mode 2: S / G
 };
 
 // Implicit-GEMM view of a causal 3D convolution over a (replicate-)padded NDHWC activation tensor: one
@@ -75,7 +86,9 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RES_STAGES = kRes ? (BLOCK_N <= 128 ? 4 : 3) : 0;
   static constexpr int RES_BYTES = RES_STAGES * kResChunkBytes;
-  static constexpr int FIXED_BYTES = RES_BYTES + kBarBytes + kEpiStageBytes + 1024;  // +1024 alignment slack
+  // epilogue staging: per-warp fp32 tiles, or (head tiles) the bf16 images of the two head tiles a CTA produces
+  static constexpr int EPI_BYTES = kHT ? 2 * kBlockM * (((BLOCK_N / 2) + 15) / 16 * 16) * 2 : kEpiStageBytes;
+  static constexpr int FIXED_BYTES = RES_BYTES + kBarBytes + EPI_BYTES + 1024;  // +1024 alignment slack
   static constexpr int STAGES_RAW = (kSmemTotal - FIXED_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
@@ -119,7 +132,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const bool is_leader = cta_rank == 0;
 
   const int64_t tile_m = (int64_t)kBlockM * kCta;
-  const int64_t num_m_blocks = kConv ? (int64_t)cg.nb * cg.tiles_t * cg.tiles_h * cg.tiles_w : (p.M + tile_m - 1) / tile_m;
+  const int64_t num_m_blocks = kConv ? (int64_t)cg.nb * cg.tiles_t * cg.tiles_h * cg.tiles_w
+                               : ((kHT && ht.fast == 2) ? ((int64_t)ht.tiles_total + kCta - 1) / kCta : (p.M + tile_m - 1) / tile_m);
   // conv: m_blk -> (batch, t-tile, h-tile, w-tile); this CTA's box origin in OUTPUT coordinates
   auto conv_origin = [&](int64_t m_blk, int& n_i, int& t0, int& h0, int& w0) {
     const int tw = (int)(m_blk % cg.tiles_w);
@@ -195,14 +209,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             ah = h0 * cg.sh + (tap / cg.kw_n) % cg.kh_n;
             at = t0 * cg.st + tap / (cg.kw_n * cg.kh_n);
           }
+          if constexpr (kHT) {
+            if (ht.fast == 2) {   // temporal view: box (64 k, T frames, G sequences) of batch b, sequence group sg
+              int64_t ti = m_blk * kCta + cta_rank;
+              if (ti >= ht.tiles_total) ti = ht.tiles_total - 1;   // odd tile count: the pair's second CTA repeats the last tile
+              at = (int32_t)(ti / ht.groups_per_batch);                          // batch
+              ah = (int32_t)(ti - (int64_t)at * ht.groups_per_batch) * ht.map.G;  // first sequence (s) of the group
+            }
+          }
           if constexpr (kCta == 1) {
             mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
             if constexpr (kConv) tma_load_5d(&tmap_a, full_bar(stage), smem_a(stage), ac, aw, ah, at, n_i);
             else tma_load_2d(&tmap_a, full_bar(stage), smem_a(stage), k0, a_row);
             tma_load_2d(&tmap_w, full_bar(stage), smem_b(stage), k0, w_row);
           } else {
-            if (is_leader) mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * 2);
+            uint32_t tx = Cfg::STAGE_BYTES * 2;
+            if constexpr (kHT) { if (ht.fast == 2) tx = 2u * (uint32_t)(ht.a_rows * kBlockK * 2 + Cfg::B_BYTES); }
+            if (is_leader) mbar_expect_tx(full_bar(stage), tx);
             if constexpr (kConv) tma_load_5d_cg2(&tmap_a, leader_full[stage], smem_a(stage), ac, aw, ah, at, n_i);
+            else if (kHT && ht.fast == 2) tma_load_5d_cg2(&tmap_a, leader_full[stage], smem_a(stage), k0, 0, ah, at, 0);
             else tma_load_2d_cg2(&tmap_a, leader_full[stage], smem_a(stage), k0, a_row);
             tma_load_2d_cg2(&tmap_w, leader_full[stage], smem_b(stage), k0, w_row);
           }
@@ -284,11 +309,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int q = warp & 3;
     const int hh = e >> 2;
     const int C = ht.heads * D;
+    const int r_loc = q * 32 + lane;                       // row inside the CTA's 128-row block
+    uint8_t* stage_h = smem_raw + (stage_base - smem_u32(smem_raw)) + hh * (kBlockM * HT::ROW_BYTES);
+    const bool store_leader = (q == 0 && lane == 0);       // issues this head's bulk stores
+    const int chunk_bytes = ht.map.TR * 128;
     int as = 0;
     uint32_t aphase = 0;
     for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int64_t m_blk = tile / num_n_blocks, n_blk = tile % num_n_blocks;
-      const int64_t row = m_blk * tile_m + cta_rank * kBlockM + q * 32 + lane;
+      const int64_t row = m_blk * tile_m + cta_rank * kBlockM + r_loc;
       mbar_wait(tmem_full_bar(as), aphase);
       tc_fence_after();
       uint32_t raw[D];
@@ -303,105 +332,135 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       __syncwarp();
       if (lane == 0) {
         // relaxed: the payload is TMEM (ordered by the fences above); a release here would wait for the previous
-        // tile's scattered global stores to drain while the MMA warp is waiting for this accumulator stage
+        // tile's global stores to drain while the MMA warp is waiting for this accumulator stage
         if constexpr (kCta == 2) mbar_arrive_cluster_relaxed(tmem_empty_bar(as), 0);
         else mbar_arrive(tmem_empty_bar(as));
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
       const int64_t col0 = n_blk * BLOCK_N + hh * D;
-      if (col0 >= p.N || row >= p.M) continue;
+      if (col0 >= p.N) continue;                            // uniform over the four warps of this head
       const int kidx = (int)((uint32_t)col0 / (uint32_t)C);
       const int head = (int)((uint32_t)col0 - (uint32_t)kidx * (uint32_t)C) / D;
       const int kind = kidx % ht.nkinds;
+      // token row -> (position in its sequence, tile, row in tile)
+      uint32_t pos, tile_i;
+      int r;
+      bool row_ok;
+      if (ht.fast != 0) {
+        tile_i = (uint32_t)(m_blk * kCta + cta_rank);
+        r = r_loc;
+        row_ok = r_loc < ht.a_rows && tile_i < (uint32_t)ht.tiles_total;
+        pos = ht.fast == 2 ? (uint32_t)r_loc % (uint32_t)ht.map.L
+                           : (tile_i % (uint32_t)ht.map.tps) * (uint32_t)ht.map.TR + (uint32_t)r_loc;
+      } else {   // (32-bit arithmetic: the host checks M < 2^31)
+        uint32_t seq;
+        const uint32_t row32 = (uint32_t)row;
+        row_ok = row < p.M;
+        if (ht.map.mode == 0) {
+          seq = row32 / (uint32_t)ht.map.L;
+          pos = row32 - seq * (uint32_t)ht.map.L;
+        } else {
+          const uint32_t ts = (uint32_t)ht.map.T * (uint32_t)ht.map.S;
+          const uint32_t b = row32 / ts;
+          const uint32_t rem = row32 - b * ts;
+          pos = rem / (uint32_t)ht.map.S;
+          seq = b * (uint32_t)ht.map.S + (rem - pos * (uint32_t)ht.map.S);
+        }
+        if (ht.map.G > 1) {
+          tile_i = seq / (uint32_t)ht.map.G;
+          r = (int)((seq - tile_i * (uint32_t)ht.map.G) * (uint32_t)ht.map.L + pos);
+        } else {
+          const uint32_t jt = pos / (uint32_t)ht.map.TR;
+          tile_i = seq * (uint32_t)ht.map.tps + jt;
+          r = (int)(pos - jt * (uint32_t)ht.map.TR);
+        }
+      }
       float x[D];
 #pragma unroll
       for (int i = 0; i < D; ++i) x[i] = __uint_as_float(raw[i]);
-      if (p.bias) {
+      if (row_ok) {
+        if (p.bias) {
 #pragma unroll
-        for (int u = 0; u < HT::U; ++u) {
-          const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col0) + u);
-          const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+          for (int u = 0; u < HT::U; ++u) {
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col0) + u);
+            const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 f = unpack_bf16x2(bw[k]);
-            x[8 * u + 2 * k] += f.x;
-            x[8 * u + 2 * k + 1] += f.y;
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = unpack_bf16x2(bw[k]);
+              x[8 * u + 2 * k] += f.x;
+              x[8 * u + 2 * k + 1] += f.y;
+            }
+          }
+        }
+        if ((ht.norm_mask >> kind) & 1u) {
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+          for (int i = 0; i < D; i += 4) { s0 += x[i] * x[i]; s1 += x[i + 1] * x[i + 1]; s2 += x[i + 2] * x[i + 2]; s3 += x[i + 3] * x[i + 3]; }
+          const float rs = rsqrtf(((s0 + s1) + (s2 + s3)) * (1.0f / D) + ht.eps);
+          // (a runtime index into the parameter struct would move the whole struct to local memory)
+          const __nv_bfloat16* w = kind == 0 ? ht.norm_w[0] : (kind == 1 ? ht.norm_w[1] : (kind == 2 ? ht.norm_w[2] : ht.norm_w[3]));
+#pragma unroll
+          for (int u = 0; u < HT::U; ++u) {
+            const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w) + u);
+            const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = unpack_bf16x2(ww[k]);
+              x[8 * u + 2 * k] *= rs * f.x;
+              x[8 * u + 2 * k + 1] *= rs * f.y;
+            }
+          }
+        }
+        if ((ht.rope_mask >> kind) & 1u) {
+          const float4* cr = reinterpret_cast<const float4*>(ht.cos + (int64_t)pos * (D / 2));
+          const float4* sr = reinterpret_cast<const float4*>(ht.sin + (int64_t)pos * (D / 2));
+#pragma unroll
+          for (int u = 0; u < HT::U; ++u) {
+            const float4 c4 = __ldg(cr + u), s4 = __ldg(sr + u);
+            const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float a = x[8 * u + 2 * i], b = x[8 * u + 2 * i + 1];
+              x[8 * u + 2 * i] = a * cc[i] - b * sn[i];
+              x[8 * u + 2 * i + 1] = b * cc[i] + a * sn[i];
+            }
           }
         }
       }
-      // token row -> (sequence position, tile, row in tile)
-      // (32-bit arithmetic: the host checks M < 2^31)
-      uint32_t seq, pos;
-      const uint32_t row32 = (uint32_t)row;
-      if (ht.map.mode == 0) {
-        seq = row32 / (uint32_t)ht.map.L;
-        pos = row32 - seq * (uint32_t)ht.map.L;
-      } else {
-        const uint32_t ts = (uint32_t)ht.map.T * (uint32_t)ht.map.S;
-        const uint32_t b = row32 / ts;
-        const uint32_t rem = row32 - b * ts;
-        pos = rem / (uint32_t)ht.map.S;
-        seq = b * (uint32_t)ht.map.S + (rem - pos * (uint32_t)ht.map.S);
+      uint8_t* gdst = ht.base + (int64_t)kidx * ht.kind_stride + (int64_t)head * ht.head_stride + (int64_t)tile_i * ht.tile_bytes;
+      if (ht.fast != 0) {
+        // the previous bulk store of this head must have finished READING the staging image before it is overwritten
+        if (store_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + hh) : "memory");
       }
-      uint32_t tile_i;
-      int r;
-      if (ht.map.G > 1) {
-        tile_i = seq / (uint32_t)ht.map.G;
-        r = (int)((seq - tile_i * (uint32_t)ht.map.G) * (uint32_t)ht.map.L + pos);
-      } else {
-        const uint32_t jt = pos / (uint32_t)ht.map.TR;
-        tile_i = seq * (uint32_t)ht.map.tps + jt;
-        r = (int)(pos - jt * (uint32_t)ht.map.TR);
-      }
-      if ((ht.norm_mask >> kind) & 1u) {
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      uint8_t* dst = ht.fast != 0 ? stage_h : gdst;
+      if (ht.fast != 0 || row_ok) {
 #pragma unroll
-        for (int i = 0; i < D; i += 4) { s0 += x[i] * x[i]; s1 += x[i + 1] * x[i + 1]; s2 += x[i + 2] * x[i + 2]; s3 += x[i + 3] * x[i + 3]; }
-        const float rs = rsqrtf(((s0 + s1) + (s2 + s3)) * (1.0f / D) + ht.eps);
-        // (a runtime index into the parameter struct would move the whole struct to local memory)
-        const __nv_bfloat16* w = kind == 0 ? ht.norm_w[0] : (kind == 1 ? ht.norm_w[1] : (kind == 2 ? ht.norm_w[2] : ht.norm_w[3]));
-#pragma unroll
-        for (int u = 0; u < HT::U; ++u) {
-          const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w) + u);
-          const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 f = unpack_bf16x2(ww[k]);
-            x[8 * u + 2 * k] *= rs * f.x;
-            x[8 * u + 2 * k + 1] *= rs * f.y;
+        for (int u = 0; u < HT::UP; ++u) {
+          uint4 o = make_uint4(0, 0, 0, 0);
+          if (u < HT::U && row_ok) {
+            o.x = pack_bf16x2(x[8 * u], x[8 * u + 1]);
+            o.y = pack_bf16x2(x[8 * u + 2], x[8 * u + 3]);
+            o.z = pack_bf16x2(x[8 * u + 4], x[8 * u + 5]);
+            o.w = pack_bf16x2(x[8 * u + 6], x[8 * u + 7]);
           }
+          if (ht.fast != 0 && r >= ht.map.TR) continue;   // (tile_rows < 128: rows past the tile are not part of its image)
+          if (u < HT::MAIN * 8) *reinterpret_cast<uint4*>(dst + (u >> 3) * chunk_bytes + sw128_off(r, u & 7)) = o;
+          else *reinterpret_cast<uint4*>(dst + HT::MAIN * chunk_bytes + tail_off(r, u - HT::MAIN * 8)) = o;
         }
       }
-      if ((ht.rope_mask >> kind) & 1u) {
-        const float4* cr = reinterpret_cast<const float4*>(ht.cos + (int64_t)pos * (D / 2));
-        const float4* sr = reinterpret_cast<const float4*>(ht.sin + (int64_t)pos * (D / 2));
-#pragma unroll
-        for (int u = 0; u < HT::U; ++u) {
-          const float4 c4 = __ldg(cr + u), s4 = __ldg(sr + u);
-          const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float a = x[8 * u + 2 * i], b = x[8 * u + 2 * i + 1];
-            x[8 * u + 2 * i] = a * cc[i] - b * sn[i];
-            x[8 * u + 2 * i + 1] = b * cc[i] + a * sn[i];
-          }
+      if (ht.fast != 0) {
+        fence_proxy_async_smem();                          // generic-proxy writes -> visible to the bulk-copy engine
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + hh) : "memory");
+        if (store_leader && tile_i < (uint32_t)ht.tiles_total) {
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(gdst)),
+                       "r"(smem_u32(stage_h)), "r"((uint32_t)ht.tile_bytes)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-      }
-      uint8_t* dst = ht.base + (int64_t)kidx * ht.kind_stride + (int64_t)head * ht.head_stride + (int64_t)tile_i * ht.tile_bytes;
-      const int chunk_bytes = ht.map.TR * 128;
-#pragma unroll
-      for (int u = 0; u < HT::UP; ++u) {
-        uint4 o = make_uint4(0, 0, 0, 0);
-        if (u < HT::U) {
-          o.x = pack_bf16x2(x[8 * u], x[8 * u + 1]);
-          o.y = pack_bf16x2(x[8 * u + 2], x[8 * u + 3]);
-          o.z = pack_bf16x2(x[8 * u + 4], x[8 * u + 5]);
-          o.w = pack_bf16x2(x[8 * u + 6], x[8 * u + 7]);
-        }
-        if (u < HT::MAIN * 8) *reinterpret_cast<uint4*>(dst + (u >> 3) * chunk_bytes + sw128_off(r, u & 7)) = o;
-        else *reinterpret_cast<uint4*>(dst + HT::MAIN * chunk_bytes + tail_off(r, u - HT::MAIN * 8)) = o;
       }
     }
+    if (ht.fast != 0 && store_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // smem must outlive the stores
   } else {
     // ===================== epilogue warps =====================
     // TMEM -> registers (thread = accumulator row) -> per-warp fp32 staging tile in smem -> re-read with
@@ -577,22 +636,52 @@ static int launch_kernel(const CUtensorMap& ta, const CUtensorMap& tw, const CUt
 }
 
 // head-tile GEMM: BLOCK_N = 2 heads, CTA pairs
+// OSB_HT_FAST=0 forces the general (per-row scattered store) head-tile epilogue: A/B measurements and tests
+static bool ht_fast_enabled() {
+  static const bool on = [] { const char* e = getenv("OSB_HT_FAST"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 template <int D>
-static int launch_gemm_ht(const osb_gemm_args& a, const HeadTileParams& ht, cudaStream_t stream) {
+static int launch_gemm_ht(const osb_gemm_args& a, HeadTileParams ht, bool allow_fast, cudaStream_t stream) {
   constexpr int BLOCK_N = 2 * D, kCta = 2;
   using Cfg = GemmCfg<BLOCK_N, kCta, false, true>;
   CUtensorMap ta, tw;
-  int rc = make_tmap_2d_bf16(&ta, a.A, a.M, a.K, a.lda, kBlockM, kBlockK);
+  int rc;
+  const TileMap& m = ht.map;
+  ht.fast = 0;
+  ht.a_rows = kBlockM;
+  if (allow_fast && ht_fast_enabled()) {
+    if (m.mode == 0 && m.G == 1 && m.TR == kBlockM && m.L % kBlockM == 0) ht.fast = 1;
+    else if (m.mode == 1 && m.tps == 1 && m.S % m.G == 0 && m.G * m.L <= m.TR && (int64_t)m.L * m.G <= kBlockM) ht.fast = 2;
+  }
+  int64_t m_rows = a.M;
+  if (ht.fast == 2) {
+    // A viewed as [k][t][s][b] (strides lda, S*lda, lda... in elements): one box = (64 k, T frames, G sequences) = the rows
+    // g*T + t of one packed temporal tile, in exactly that order.  Out-of-range coordinates never occur (S % G == 0).
+    const uint64_t B = (uint64_t)(a.M / ((int64_t)m.S * m.T));
+    const uint64_t dims[5] = {(uint64_t)a.K, (uint64_t)m.T, (uint64_t)m.S, B, 1};
+    const uint64_t row_b = (uint64_t)a.lda * 2;
+    const uint64_t str[4] = {(uint64_t)m.S * row_b, row_b, (uint64_t)m.T * m.S * row_b, (uint64_t)m.T * m.S * row_b * B};
+    const uint32_t box[5] = {(uint32_t)kBlockK, (uint32_t)m.T, (uint32_t)m.G, 1, 1};
+    const uint32_t es[5] = {1, 1, 1, 1, 1};
+    rc = make_tmap_5d_bf16(&ta, a.A, dims, str, box, es);
+    ht.a_rows = m.G * m.L;
+    ht.groups_per_batch = m.S / m.G;
+    m_rows = (int64_t)ht.tiles_total * kBlockM;   // virtual rows: one 128-row accumulator block per head tile
+  } else {
+    rc = make_tmap_2d_bf16(&ta, a.A, a.M, a.K, a.lda, kBlockM, kBlockK);
+  }
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tw, a.W, a.N, a.K, a.ldw, Cfg::LOAD_N, kBlockK);
   if (rc) return rc;
   GemmEpilogueParams p = {};
   p.bias = static_cast<const __nv_bfloat16*>(a.bias);
-  p.M = a.M; p.N = a.N; p.K = a.K;
-  p.group_rows = a.M;
+  p.M = m_rows; p.N = a.N; p.K = a.K;
+  p.group_rows = m_rows;
   p.epilogue = OSB_EPI_BIAS;
   const int64_t tile_m = (int64_t)kBlockM * kCta;
-  const int64_t tiles = ((a.M + tile_m - 1) / tile_m) * ((a.N + BLOCK_N - 1) / BLOCK_N);
+  const int64_t tiles = ((m_rows + tile_m - 1) / tile_m) * ((a.N + BLOCK_N - 1) / BLOCK_N);
   ConvGeom cg = {};
   return launch_kernel<BLOCK_N, kCta, false, false, true>(ta, tw, ta, p, cg, tiles, stream, ht);
 }
@@ -879,6 +968,8 @@ extern "C" int osb_gemm_head_tiles(const osb_gemm_args* args, const osb_head_til
   ht.kind_stride = t.kind_stride; ht.head_stride = t.head_stride;
   ht.map.mode = m.mode; ht.map.L = m.L; ht.map.S = m.S; ht.map.T = m.T; ht.map.G = m.G; ht.map.tps = m.tps; ht.map.TR = m.tile_rows;
   ht.tile_bytes = (int32_t)tile_bytes;
+  ht.tiles_total = (int32_t)tph;
+  OSB_REQUIRE(tph < (1ll << 31), "osb_gemm_head_tiles: too many tiles");
   ht.heads = t.num_heads; ht.nkinds = t.nkinds;
   ht.norm_mask = t.norm_mask; ht.rope_mask = t.rope_mask;
   for (int k = 0; k < 4; ++k) {
@@ -891,7 +982,8 @@ extern "C" int osb_gemm_head_tiles(const osb_gemm_args* args, const osb_head_til
   OSB_REQUIRE(t.rope_mask == 0 || (t.rope_cos && t.rope_sin && ((reinterpret_cast<uintptr_t>(t.rope_cos) | reinterpret_cast<uintptr_t>(t.rope_sin)) & 15) == 0),
               "osb_gemm_head_tiles: RoPE enabled but the cos / sin tables are missing or not 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (D == 64) return launch_gemm_ht<64>(a, ht, s);
-  if (D == 72) return launch_gemm_ht<72>(a, ht, s);
-  return launch_gemm_ht<128>(a, ht, s);
+  const bool allow_fast = (t.reserved & 1) == 0;   // bit 0 of `reserved`: force the general (per-row store) epilogue
+  if (D == 64) return launch_gemm_ht<64>(a, ht, allow_fast, s);
+  if (D == 72) return launch_gemm_ht<72>(a, ht, allow_fast, s);
+  return launch_gemm_ht<128>(a, ht, allow_fast, s);
 }

@@ -117,21 +117,6 @@ class SelfAttention(nn.Module):
             self.v_proj = nn.Linear(dim, dim, bias=qkv_bias)
         self.norm = QKNorm(dim // num_heads)
         self.proj = nn.Linear(dim, dim)
-        self._packed = None
-
-    def _apply(self, fn, *a, **k):
-        self._packed = None
-        return super()._apply(fn, *a, **k)
-
-    def qkv_weights(self):
-        """[3C, C] weight and [3C] bias in q|k|v row order for ONE GEMM, whichever way the checkpoint stores them."""
-        if self.fused_qkv:
-            return self.qkv.weight, self.qkv.bias
-        if self._packed is None:
-            w = torch.cat([self.q_proj.weight, self.k_proj.weight, self.v_proj.weight], 0).contiguous()
-            b = None if self.q_proj.bias is None else torch.cat([self.q_proj.bias, self.k_proj.bias, self.v_proj.bias], 0).contiguous()
-            self._packed = (w, b)
-        return self._packed
 
 
 @dataclass
@@ -142,6 +127,9 @@ class ModulationOut:
 
 
 class Modulation(nn.Module):
+    """Parameter container (layers.py:179-192); the processors read `lin` / `multiplier` and run the projection on
+    osb200.  `forward` keeps the reference's return contract for callers outside the block path."""
+
     def __init__(self, dim: int, double: bool):
         super().__init__()
         self.is_double = double
@@ -149,10 +137,8 @@ class Modulation(nn.Module):
         self.lin = nn.Linear(dim, self.multiplier * dim, bias=True)
 
     def forward(self, vec: Tensor):
-        """layers.py:186-192; returns fp32 [B, C] row views (row stride = multiplier*C) the kernels consume directly."""
-        out = _linear(torch.nn.functional.silu(vec).contiguous(), self.lin).float()
-        c = out.chunk(self.multiplier, dim=-1)
-        return ModulationOut(*c[:3]), (ModulationOut(*c[3:]) if self.is_double else None)
+        out = _linear(torch.nn.functional.silu(vec).contiguous(), self.lin)[:, None, :].chunk(self.multiplier, dim=-1)
+        return ModulationOut(*out[:3]), (ModulationOut(*out[3:]) if self.is_double else None)
 
 
 def _check(x: Tensor):
@@ -166,23 +152,63 @@ def _rope(pe):
     return rope_tables(pe)
 
 
-class DoubleStreamBlockProcessor:
+class _ProcessorBase:
+    """What both processors share.  A processor holds NO model weights and touches only attributes the reference's own
+    block classes have (`opensora/models/mmdit/layers.py:138-176,256-306,337-388`), so it can be installed with
+    `block.set_processor(...)` on the reference's DoubleStreamBlock / SingleStreamBlock objects as well as on this
+    package's.  Derived tensors (q|k|v weights concatenated for checkpoints with `fused_qkv=False`) are cached per
+    block, keyed by the identity and version of the source parameters, so `.to()` / `load_state_dict` invalidate them."""
+
+    def __init__(self):
+        import weakref
+
+        self._cache = weakref.WeakKeyDictionary()
+
+    def _cached(self, block: nn.Module, name: str, sources, build):
+        sig = tuple((t.data_ptr(), t._version, t.dtype, t.device) for t in sources if t is not None)
+        ent = self._cache.setdefault(block, {})
+        hit = ent.get(name)
+        if hit is None or hit[0] != sig:
+            ent[name] = hit = (sig, build())
+        return hit[1]
+
+    def _qkv(self, block: nn.Module, sa: nn.Module, name: str):
+        """[3C, C] weight and [3C] bias in q|k|v row order for ONE GEMM, whichever way the checkpoint stores them."""
+        if getattr(sa, "fused_qkv", hasattr(sa, "qkv")):
+            return sa.qkv.weight, sa.qkv.bias
+        ws = (sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight)
+        bs = (sa.q_proj.bias, sa.k_proj.bias, sa.v_proj.bias)
+        return self._cached(block, name, ws + bs, lambda: (
+            torch.cat(ws, 0).contiguous(), None if bs[0] is None else torch.cat(bs, 0).contiguous()))
+
+    @staticmethod
+    def _modulation(osb, mod: nn.Module, vec: Tensor):
+        """layers.py:186-192 on osb200: lin(silu(vec)) -> fp32 [B, C] row views (row stride multiplier*C) the kernels take
+        as shift / scale / gate."""
+        out = osb.gemm(torch.nn.functional.silu(vec).contiguous(), mod.lin.weight, mod.lin.bias).float()
+        mult = getattr(mod, "multiplier", None) or (mod.lin.out_features // mod.lin.in_features)
+        c = out.chunk(mult, dim=-1)
+        return ModulationOut(*c[:3]), (ModulationOut(*c[3:6]) if mult >= 6 else None)
+
+
+class DoubleStreamBlockProcessor(_ProcessorBase):
     """osb200 implementation of layers.py:195-253."""
 
     def __call__(self, attn: nn.Module, img: Tensor, txt: Tensor, vec: Tensor, pe) -> tuple[Tensor, Tensor]:
         osb = _check(img)
         B, Li, C = img.shape
         Lt = txt.shape[1]
-        L, H, D = Lt + Li, attn.num_heads, attn.head_dim
-        im1, im2 = attn.img_mod(vec)
-        tm1, tm2 = attn.txt_mod(vec)
+        L, H = Lt + Li, attn.num_heads
+        D = C // H
+        im1, im2 = self._modulation(osb, attn.img_mod, vec)
+        tm1, tm2 = self._modulation(osb, attn.txt_mod, vec)
         img2, txt2 = img.reshape(B * Li, C).contiguous(), txt.reshape(B * Lt, C).contiguous()
         xi = osb.ln_modulate(img2, im1.shift, im1.scale, group_rows=Li)
         xt = osb.ln_modulate(txt2, tm1.shift, tm1.scale, group_rows=Lt)
         # q|k|v of both streams land in ONE joint [B*(Lt+Li), 3C] buffer in txt-then-img token order (layers.py:240-242)
         qkv = torch.empty(B * L, 3 * C, dtype=img.dtype, device=img.device)
-        wi, bi = attn.img_attn.qkv_weights()
-        wt, bt = attn.txt_attn.qkv_weights()
+        wi, bi = self._qkv(attn, attn.img_attn, "img_qkv")
+        wt, bt = self._qkv(attn, attn.txt_attn, "txt_qkv")
         for b in range(B):
             osb.gemm(xt[b * Lt:(b + 1) * Lt], wt, bt, out=qkv[b * L:b * L + Lt])
             osb.gemm(xi[b * Li:(b + 1) * Li], wi, bi, out=qkv[b * L + Lt:(b + 1) * L])
@@ -239,17 +265,30 @@ class DoubleStreamBlock(nn.Module):
         return self.processor(self, img, txt, vec, pe)
 
 
-class SingleStreamBlockProcessor:
+class SingleStreamBlockProcessor(_ProcessorBase):
     """osb200 implementation of layers.py:309-334."""
+
+    def _split_weights(self, blk: nn.Module):
+        """(W_qkv [3C,C], b_qkv, W_mlp [4C,C], b_mlp): row views of linear1, or packed from q_proj / k_proj / v_mlp."""
+        C = blk.linear2.out_features
+        if getattr(blk, "fused_qkv", hasattr(blk, "linear1")):
+            w, b = blk.linear1.weight, blk.linear1.bias
+            return w[:3 * C], b[:3 * C], w[3 * C:], b[3 * C:]
+        src = (blk.q_proj.weight, blk.k_proj.weight, blk.v_mlp.weight, blk.q_proj.bias, blk.k_proj.bias, blk.v_mlp.bias)
+        wq, bq = self._cached(blk, "qkv", src, lambda: (
+            torch.cat([blk.q_proj.weight, blk.k_proj.weight, blk.v_mlp.weight[:C]], 0).contiguous(),
+            torch.cat([blk.q_proj.bias, blk.k_proj.bias, blk.v_mlp.bias[:C]], 0).contiguous()))
+        return wq, bq, blk.v_mlp.weight[C:], blk.v_mlp.bias[C:]
 
     def __call__(self, attn: nn.Module, x: Tensor, vec: Tensor, pe) -> Tensor:
         osb = _check(x)
         B, L, C = x.shape
-        H, D, M4 = attn.num_heads, attn.head_dim, attn.mlp_hidden_dim
-        mod, _ = attn.modulation(vec)
+        H = attn.num_heads
+        D, M4 = C // H, attn.linear2.in_features - C
+        mod, _ = self._modulation(osb, attn.modulation, vec)
         x2 = x.reshape(B * L, C).contiguous()
         xm = osb.ln_modulate(x2, mod.shift, mod.scale, group_rows=L)
-        wq, bq, wm, bm = attn.split_weights()
+        wq, bq, wm, bm = self._split_weights(attn)
         qkv = osb.gemm(xm, wq, bq)                                               # [B*L, 3C]
         cat = torch.empty(B * L, C + M4, dtype=x.dtype, device=x.device)         # [attn | gelu(mlp)] side by side
         osb.gemm(xm, wm, bm, epilogue=osb.EPI_BIAS_GELU_TANH, out=cat[:, C:])
@@ -283,24 +322,7 @@ class SingleStreamBlock(nn.Module):
         self.pre_norm = nn.LayerNorm(hidden_size, elementwise_affine=False, eps=1e-6)
         self.mlp_act = nn.GELU(approximate="tanh")
         self.modulation = Modulation(hidden_size, double=False)
-        self._packed = None
         self.set_processor(SingleStreamBlockProcessor())
-
-    def _apply(self, fn, *a, **k):
-        self._packed = None
-        return super()._apply(fn, *a, **k)
-
-    def split_weights(self):
-        """(W_qkv [3C,C], b_qkv, W_mlp [4C,C], b_mlp): row views of linear1, or packed from q_proj/k_proj/v_mlp."""
-        C = self.hidden_size
-        if self.fused_qkv:
-            w, b = self.linear1.weight, self.linear1.bias
-            return w[:3 * C], b[:3 * C], w[3 * C:], b[3 * C:]
-        if self._packed is None:
-            wq = torch.cat([self.q_proj.weight, self.k_proj.weight, self.v_mlp.weight[:C]], 0).contiguous()
-            bq = torch.cat([self.q_proj.bias, self.k_proj.bias, self.v_mlp.bias[:C]], 0).contiguous()
-            self._packed = (wq, bq, self.v_mlp.weight[C:], self.v_mlp.bias[C:])
-        return self._packed
 
     def set_processor(self, processor) -> None:
         self.processor = processor

@@ -440,7 +440,7 @@ class HeadTiles:
 
 
 def gemm_head_tiles(a, w, bias, tiles: HeadTiles, *, nkinds: int, norm_w=(), rope=None, rope_kinds: int = 0,
-                    eps: float = 1e-6, kind0: int = 0):
+                    eps: float = 1e-6, kind0: int = 0, general: bool = False):
     """tiles[kind0 + n // C] = head_tiles(a @ w.T + bias): each output row is split into heads; kinds listed in
     `norm_w` (bf16 [D] or None per kind) get per-head RMSNorm, kinds in the `rope_kinds` bit mask get interleaved-pair
     RoPE by token position from `rope` = (cos, sin) fp32 [L, D/2]; one rounding to bf16 at the row's place in its tile."""
@@ -460,6 +460,7 @@ def gemm_head_tiles(a, w, bias, tiles: HeadTiles, *, nkinds: int, norm_w=(), rop
     t.tiles = tiles.kind_ptr(kind0)
     t.kind_stride, t.head_stride, t.map = tiles.kind_stride, tiles.head_stride, tiles.map
     t.num_heads, t.head_dim, t.nkinds = tiles.heads, tiles.head_dim, nkinds
+    t.reserved = 1 if general else 0   # force the general per-row-store epilogue (tests / A-B)
     mask = 0
     for i, nw in enumerate(norm_w):
         if nw is not None:

@@ -336,7 +336,7 @@ def _seq_pos(m, rows, device):
     return b * m.S + rem % m.S, rem // m.S
 
 
-def gemm_head_tiles(a, w, bias, tiles, *, nkinds, norm_w=(), rope=None, rope_kinds=0, eps=1e-6, kind0=0):
+def gemm_head_tiles(a, w, bias, tiles, *, nkinds, norm_w=(), rope=None, rope_kinds=0, eps=1e-6, kind0=0, general=False):
     for t, n in ((a, "a"), (w, "w"), (bias, "bias")):
         _need(t, torch.bfloat16, n)
     M, K = a.shape
@@ -365,7 +365,8 @@ def gemm_head_tiles(a, w, bias, tiles, *, nkinds, norm_w=(), rope=None, rope_kin
     return tiles
 
 
-def attn_tiles(q, kv, out, *, q_kind=0, k_kind=1, v_kind=2, Lk, num_seqs, kv_lens=None, softmax_scale=None):
+def attn_tiles(q, kv, out, *, q_kind=0, k_kind=1, v_kind=2, Lk, num_seqs, kv_lens=None, softmax_scale=None,
+               out_scatter=None, out_ld=None):
     H, D = q.heads, q.head_dim
     m = q.map
     scale = softmax_scale if softmax_scale is not None else D ** -0.5

@@ -64,7 +64,7 @@ def read_tiles(tiles, kind):
     return out.view(torch.bfloat16)
 
 
-def _self_case(mode, B, T, S, H, D, seed=0):
+def _self_case(mode, B, T, S, H, D, seed=0, general=False):
     """One STDiT3-style self-attention: tokens frame-major [B, T, S]; mode 0 attends over S, mode 1 over T (with RoPE)."""
     import osb200 as osb
 
@@ -84,7 +84,7 @@ def _self_case(mode, B, T, S, H, D, seed=0):
     tm = osb.tile_map(0, S) if mode == 0 else osb.tile_map(1, T, S, T)
     tiles = osb.HeadTiles(R, tm, 3, H, D, dev)
     osb.gemm_head_tiles(x, w, bias, tiles, nkinds=3, norm_w=(qn, kn, None), rope=(cos, sin) if mode == 1 else None,
-                        rope_kinds=0b011)
+                        rope_kinds=0b011, general=general)
     out = torch.full((R, C), float("nan"), dtype=torch.bfloat16, device=dev)
     nseq = B * T if mode == 0 else B * S
     osb.attn_tiles(tiles, tiles, out, Lk=L, num_seqs=nseq)
@@ -132,6 +132,22 @@ def _self_case(mode, B, T, S, H, D, seed=0):
 ])
 def test_self_attention_tiles(mode, B, T, S, H, D):
     _self_case(mode, B, T, S, H, D)
+
+
+@pytest.mark.parametrize("mode,B,T,S,H,D", [
+    (0, 1, 3, 256, 4, 72), (1, 1, 64, 8, 4, 72), (1, 2, 16, 16, 2, 72), (1, 1, 100, 6, 2, 72), (0, 1, 2, 256, 2, 128),
+])
+def test_general_epilogue_matches(mode, B, T, S, H, D):
+    """Shapes the aligned fast path (staged tile image + bulk store, strided TMA view for the temporal case) takes by
+    default, forced through the general per-row-store epilogue: both must produce the same tiles."""
+    _self_case(mode, B, T, S, H, D, general=True)
+
+
+def test_temporal_odd_tile_count_and_batch():
+    """Temporal fast path with an odd number of tiles per head (the pair's second CTA idles on the last tile) and B > 1
+    (tile -> (batch, sequence group) decomposition of the strided TMA view)."""
+    _self_case(1, 3, 64, 6, 2, 72)      # 3 batches x 3 groups = 9 tiles
+    _self_case(1, 1, 32, 20, 2, 72)     # G = 4: 5 tiles
 
 
 def test_softmax_large_logits_rescale():

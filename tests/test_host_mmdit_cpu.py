@@ -75,3 +75,51 @@ def test_processor_hook_is_the_plugin_point(fake_osb):
                 timesteps=torch.tensor([0.5]), y_vec=torch.randn(1, 96).to(bf), cond=torch.randn(1, 16, 68).to(bf),
                 guidance=torch.tensor([4.0]))
     assert len(seen) == CFG["depth"] and out.shape == (1, 16, 64) and torch.isfinite(out.float()).all()
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_processors_run_on_the_reference_own_blocks(fake_osb, fused):
+    """the processors are installed with `set_processor` on block objects built from the REFERENCE's
+    own source (`/root/reference/opensora/models/mmdit/layers.py`, executed by path) - classes that have only the
+    reference's attributes - and must reproduce what those blocks compute with their stock processors."""
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        pytest.skip("reference checkout not present (GPU box)")
+    R, Rmath, _ = ref_loader.load_mmdit()
+    from opensora.models.mmdit.layers import DoubleStreamBlockProcessor, SingleStreamBlockProcessor
+
+    torch.manual_seed(5)
+    C, H, B, Lt, Li = 256, 2, 2, 24, 48
+    dbl = R.DoubleStreamBlock(C, H, mlp_ratio=4.0, qkv_bias=True, fused_qkv=fused).eval()
+    sgl = R.SingleStreamBlock(C, H, mlp_ratio=4.0, fused_qkv=fused).eval()
+    with torch.no_grad():
+        for blk in (dbl, sgl):
+            for n, p in blk.named_parameters():
+                p.copy_(torch.randn_like(p) * (0.2 if n.endswith("scale") else 0.05) + (1.0 if n.endswith("scale") else 0.0))
+    ids = torch.zeros(B, Lt + Li, 3)
+    ids[:, Lt:, 0] = torch.arange(Li) // 16
+    ids[:, Lt:, 1] = (torch.arange(Li) // 4) % 4
+    ids[:, Lt:, 2] = torch.arange(Li) % 4
+    pe = R.EmbedND(dim=C // H, theta=10000, axes_dim=[16, 56, 56])(ids)
+    bf = torch.bfloat16
+    img, txt, vec = torch.randn(B, Li, C).to(bf), torch.randn(B, Lt, C).to(bf), torch.randn(B, C).to(bf)
+    with torch.no_grad():
+        ref_i, ref_t = dbl(img.float(), txt.float(), vec.float(), pe)                  # stock processor, fp32
+        ref_x = sgl(torch.cat((txt, img), 1).float(), vec.float(), pe)
+        dbl_b, sgl_b = dbl.to(bf), sgl.to(bf)
+        noise_i, _ = dbl_b(img, txt, vec, pe)                                          # the reference's own bf16 path
+        dbl_b.set_processor(DoubleStreamBlockProcessor())
+        sgl_b.set_processor(SingleStreamBlockProcessor())
+        out_i, out_t = dbl_b(img, txt, vec, pe)
+        out_x = sgl_b(torch.cat((txt, img), 1), vec, pe)
+        # cached packed weights follow the parameters (a second call after an in-place update must see the new values)
+        if not fused:
+            sgl_b.q_proj.weight.mul_(1.0)
+            sgl_b(torch.cat((txt, img), 1), vec, pe)
+    rn = rel_l2(noise_i.float(), ref_i)
+    for got, ref in ((out_i, ref_i), (out_t, ref_t), (out_x, ref_x)):
+        r = rel_l2(got.float(), ref)
+        assert got.shape == ref.shape and r < max(2.0 * rn, 6e-3), (r, rn)
+    names = [c[0] for c in fake_osb.calls]
+    assert names.count("attn_short") == (2 if fused else 3) and "ln_modulate" in names
