@@ -171,7 +171,9 @@ int64_t osb_head_tiles_per_head(const osb_tile_map* map, int64_t rows);
 typedef struct osb_attn_tiles_args {
   const void* q_tiles; const void* k_tiles; const void* v_tiles;  /* tile 0 of head 0 of each operand                */
   int64_t q_head_stride, kv_head_stride;                          /* bytes between heads                            */
-  osb_tile_map q_map;        /* rows of `out` <-> q tiles; key set i belongs to sequence i (G == 1) or tile i (G > 1) */
+  osb_tile_map q_map;        /* rows of `out` <-> q tiles; key set i belongs to sequence i (G == 1) or tile i (G > 1).
+                                The map may differ from the one the tiles were written with in `mode` only (tiles produced
+                                from a transposed [B, S, T] stream with mode 0, output rows frame-major with mode 1)      */
   int32_t kv_tile_rows;      /* rows per key / value tile (multiple of 16, <= 128)                                  */
   int32_t kv_tiles_per_set;  /* key tiles per sequence: ceil(Lk / kv_tile_rows) (1 for packed sequences)            */
   int32_t Lk;                /* keys per sequence                                                                   */
@@ -203,7 +205,11 @@ typedef struct osb_scatter {
                      1: J is split over the P ranks: row (b, i, j) goes to rank p = j / (J/P), row
                         (b*(P*I) + rank*I + i) * (J/P) + j % (J/P) of its buffer   ([B, Tl, S] -> [B, T, S/P]);
                      2: I is split: row (b, i, j) goes to rank p = i / (I/P), row
-                        (b*(I/P) + i % (I/P)) * (P*J) + rank*J + j of its buffer   ([B, T, Sl] -> [B, T/P, S])       */
+                        (b*(I/P) + i % (I/P)) * (P*J) + rank*J + j of its buffer   ([B, T, Sl] -> [B, T/P, S]);
+                     3: no exchange, rows transposed: (b, i, j) -> row (b*J + j)*I + i of peer[rank]
+                        ([B, T, S] -> [B, S, T]: temporal sequences become contiguous row blocks for the QKV GEMM);
+                     4: mode 1 with the destination transposed: rank p = j / (J/P) gets row
+                        (b*(J/P) + j % (J/P)) * (P*I) + rank*I + i   ([B, Tl, S] -> [B, S/P, T])                     */
   int32_t P, rank, I, J;
   int32_t reserved[3];
   void* peer[OSB_MAX_PEERS];   /* base of the destination buffer on every rank (peer[rank] is the local one)           */

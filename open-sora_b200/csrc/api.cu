@@ -134,12 +134,12 @@ int make_tmap_5d_bf16(CUtensorMap* map, const void* base, const uint64_t dims[5]
 int make_row_scatter(RowScatter* dst, const osb_scatter* src, int64_t rows, const char* who) {
   *dst = RowScatter();
   if (src == nullptr || src->mode == 0) return OSB_OK;
-  if (src->mode != 1 && src->mode != 2) { set_error("%s: unknown scatter mode %d", who, src->mode); return OSB_ERR_INVALID; }
+  if (src->mode < 1 || src->mode > 4) { set_error("%s: unknown scatter mode %d", who, src->mode); return OSB_ERR_INVALID; }
   if (src->P < 1 || src->P > OSB_MAX_PEERS || src->rank < 0 || src->rank >= src->P || src->I <= 0 || src->J <= 0) {
     set_error("%s: bad scatter (P %d rank %d I %d J %d)", who, src->P, src->rank, src->I, src->J);
     return OSB_ERR_INVALID;
   }
-  const int split = src->mode == 1 ? src->J : src->I;
+  const int split = src->mode == 2 ? src->I : (src->mode == 3 ? src->P : src->J);
   if (split % src->P != 0 || rows % ((int64_t)src->I * src->J) != 0 || rows >= (1ll << 31)) {
     set_error("%s: scatter of [*, %d, %d] rows over %d ranks does not divide (%lld rows)", who, src->I, src->J, src->P, (long long)rows);
     return OSB_ERR_INVALID;

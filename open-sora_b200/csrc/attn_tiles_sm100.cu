@@ -18,12 +18,14 @@
 //
 // Replaces: opensora/models/mmdit/math.py:22-36 (attention) for the STDiT3 Attention / MultiHeadCrossAttention
 // restated in SURVEY.md App. A; QK-RMSNorm + RoPE (layers.py:102-135, math.py:60-65) moved into the GEMM epilogue.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tiles.cuh"
 
 namespace osb {
 
-constexpr int kTAThreads = 384;   // 3 warpgroups: softmax 0, softmax 1, {loader, issuer, 2 idle warps}
+constexpr int kTAThreads = 384;   // 3 warpgroups: softmax 0, softmax 1, {loader, issuer, 2 output store warps}
 constexpr int kTALoaderWarp = 8;
 constexpr int kTAIssuerWarp = 9;
 constexpr int kTAMaxStages = 4;
@@ -47,8 +49,10 @@ struct TileAttnParams {
   int64_t num_pairs;
   int32_t nst;              // K/V ring stages
   int32_t resident;         // shared mode and nkb <= nst: key tiles stay across the pairs of one (set, head)
-  int32_t off_kv, off_bar;  // shared memory carve-up
+  int32_t off_kv, off_out, off_bar;  // shared memory carve-up
   RowScatter out_sc;        // sequence parallel: output rows go straight to the consuming rank's buffer
+  int32_t exp_flags;        // OSB_TA_EXP (timing experiments only, results become wrong): 1 no PV tail MMA, 2 no PV MMAs,
+                            // 4 no S tail MMA, 8 no exp2 (P = 0), 16 no output epilogue, 32 no S MMAs (any value: generic PV issue loop)
 };
 
 #ifdef OSB_TA_TRACE
@@ -96,7 +100,9 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
   auto o_full = [&](int s) { return bar0 + 64u + 8u * s; };
   auto kv_full = [&](int st) { return bar0 + 80u + 8u * st; };
   auto kv_empty = [&](int st) { return bar0 + 80u + 8u * kTAMaxStages + 8u * st; };
-  const uint32_t tmem_slot = bar0 + 80u + 16u * kTAMaxStages;
+  auto out_full = [&](int s) { return bar0 + 80u + 16u * kTAMaxStages + 8u * s; };
+  auto out_empty = [&](int s) { return bar0 + 96u + 16u * kTAMaxStages + 8u * s; };
+  const uint32_t tmem_slot = bar0 + 112u + 16u * kTAMaxStages;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   if (warp == kTAIssuerWarp) {
@@ -104,6 +110,7 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
       for (int s = 0; s < 2; ++s) {
         mbar_init(q_full(s), 1); mbar_init(q_empty(s), 1); mbar_init(s_full(s), 1);
         mbar_init(p_full(s), 128); mbar_init(o_full(s), 1);
+        mbar_init(out_full(s), 128); mbar_init(out_empty(s), 1);
       }
       for (int st = 0; st < kTAMaxStages; ++st) { mbar_init(kv_full(st), 1); mbar_init(kv_empty(st), 1); }
       fence_barrier_init();
@@ -178,7 +185,7 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
     const uint32_t t_s = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(slot * 256);
     const uint32_t t_o = t_s + 128;
     const float sc = p.scale_log2;
-    uint32_t n_s = 0, n_o = 0;
+    uint32_t n_s = 0, n_o = 0, n_out = 0;
     TA_TR_DECL
     for (int pair = pair_lo; pair < pair_hi; ++pair) {
       PairJob j;
@@ -272,7 +279,7 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
         for (int c = 0; c < 4; ++c) {
           if (c * 32 >= ncol) continue;   // warp-uniform: the PV MMA does not read these columns
           uint32_t pk[16];
-          if (!live[c] || !some) {
+          if (!live[c] || !some || (p.exp_flags & 8)) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) pk[e] = 0u;
           } else if (blo <= c * 32 && bhi >= c * 32 + 32) {
@@ -310,6 +317,7 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
       tc_fence_after();
       if ((warp & 3) == 0) TA_TR(slot, 14);
       const float inv = l > 0.f ? 1.0f / l : 0.f;
+      if (p.exp_flags & 16) continue;
       uint32_t o[Cfg::U * 8];
 #pragma unroll
       for (int c = 0; c + 32 <= D; c += 32) tmem_ld_32x32b_x32(t_o + c, reinterpret_cast<uint32_t(&)[32]>(o[c]));
@@ -322,6 +330,13 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
       tmem_ld_wait();
       tc_fence_before();
       if ((warp & 3) == 0) TA_TR(slot, 15);
+      // Output: the thread's row goes through a shared-memory staging tile so that the global stores are issued
+      // row-contiguously (U consecutive lanes write one row's D*2 bytes; a thread-per-row store would touch 32 lines per
+      // instruction and costs ~70 LSU cycles each).  Row pointers are resolved once per row (sequence-parallel rows may
+      // live in a peer's buffer).
+      uint8_t* stg = smem + p.off_out + slot * (128 * D * 2 + 128 * 8);
+      unsigned long long* rowptr = reinterpret_cast<unsigned long long*>(stg + 128 * D * 2);
+      unsigned long long my_ptr = 0ull;
       if (valid) {
         int64_t orow_i = row_of_token(p.qmap, seq, pos);
         __nv_bfloat16* obase = p.out;
@@ -330,22 +345,66 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
           scatter_row(p.out_sc, orow_i, peer, orow_i);
           obase = static_cast<__nv_bfloat16*>(scatter_base(p.out_sc, peer));
         }
-        __nv_bfloat16* orow = obase + orow_i * p.out_ld + (int64_t)j_head * D;
-#pragma unroll
-        for (int u = 0; u < Cfg::U; ++u) {
-          uint4 w;
-          if (l > 0.f) {
-            w.x = pack_bf16x2(__uint_as_float(o[8 * u]) * inv, __uint_as_float(o[8 * u + 1]) * inv);
-            w.y = pack_bf16x2(__uint_as_float(o[8 * u + 2]) * inv, __uint_as_float(o[8 * u + 3]) * inv);
-            w.z = pack_bf16x2(__uint_as_float(o[8 * u + 4]) * inv, __uint_as_float(o[8 * u + 5]) * inv);
-            w.w = pack_bf16x2(__uint_as_float(o[8 * u + 6]) * inv, __uint_as_float(o[8 * u + 7]) * inv);
-          } else {
-            w = make_uint4(0, 0, 0, 0);   // no valid key: zeros, never 0 * garbage
-          }
-          *reinterpret_cast<uint4*>(orow + u * 8) = w;
-        }
+        my_ptr = reinterpret_cast<unsigned long long>(obase + orow_i * p.out_ld + (int64_t)j_head * D);
       }
+      if (p.off_out < 0) {   // no room for a staging tile (large head_dim): each thread stores its own row
+        if (my_ptr != 0ull) {
+#pragma unroll
+          for (int u = 0; u < Cfg::U; ++u) {
+            uint4 w = make_uint4(0, 0, 0, 0);
+            if (l > 0.f) {
+              w.x = pack_bf16x2(__uint_as_float(o[8 * u]) * inv, __uint_as_float(o[8 * u + 1]) * inv);
+              w.y = pack_bf16x2(__uint_as_float(o[8 * u + 2]) * inv, __uint_as_float(o[8 * u + 3]) * inv);
+              w.z = pack_bf16x2(__uint_as_float(o[8 * u + 4]) * inv, __uint_as_float(o[8 * u + 5]) * inv);
+              w.w = pack_bf16x2(__uint_as_float(o[8 * u + 6]) * inv, __uint_as_float(o[8 * u + 7]) * inv);
+            }
+            *reinterpret_cast<uint4*>(my_ptr + (unsigned long long)(u * 16)) = w;
+          }
+        }
+        continue;
+      }
+      mbar_wait(out_empty(slot), (n_out & 1) ^ 1);   // the store warp is done reading the previous job's tile
+      ++n_out;
+      if ((warp & 3) == 0) TA_TR(slot, 17);
+      rowptr[r] = my_ptr;
+#pragma unroll
+      for (int u = 0; u < Cfg::U; ++u) {
+        uint4 w = make_uint4(0, 0, 0, 0);   // no valid key: zeros, never 0 * garbage
+        if (l > 0.f) {
+          w.x = pack_bf16x2(__uint_as_float(o[8 * u]) * inv, __uint_as_float(o[8 * u + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o[8 * u + 2]) * inv, __uint_as_float(o[8 * u + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o[8 * u + 4]) * inv, __uint_as_float(o[8 * u + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o[8 * u + 6]) * inv, __uint_as_float(o[8 * u + 7]) * inv);
+        }
+        *reinterpret_cast<uint4*>(stg + r * (D * 2) + u * 16) = w;
+      }
+      mbar_arrive(out_full(slot));   // release: the staged tile and the row pointers are visible to the store warp
       if ((warp & 3) == 0) TA_TR(slot, 16);
+    }
+  } else if (warp >= 10) {
+    // =========================================== output store warps (one per slot) ===========================================
+    // The softmax warpgroup stages a finished [128 x D] bf16 output tile in shared memory and goes on with its next job;
+    // this warp writes the tile out row-contiguously (U consecutive lanes cover one row's D*2 bytes) - to this GPU's
+    // `out`, or (sequence parallel) straight into the consuming rank's buffer over NVLink.
+    const int slot = warp - 10;
+    const int lane = tid & 31;
+    const uint8_t* stg = smem + p.off_out + slot * (128 * D * 2 + 128 * 8);
+    const unsigned long long* rowptr = reinterpret_cast<const unsigned long long*>(stg + 128 * D * 2);
+    uint32_t n_out = 0;
+    for (int pair = pair_lo; pair < pair_hi; ++pair) {
+      PairJob j;
+      decode(pair, j);
+      if (!(slot ? j.act[1] : j.act[0])) continue;
+      if ((p.exp_flags & 16) || p.off_out < 0) continue;
+      mbar_wait(out_full(slot), n_out & 1); ++n_out;
+#pragma unroll 4
+      for (int c = lane; c < 128 * Cfg::U; c += 32) {
+        const int row = c / Cfg::U, u = c - row * Cfg::U;
+        const unsigned long long dst = rowptr[row];
+        if (dst != 0ull) *reinterpret_cast<uint4*>(dst + (unsigned long long)(u * 16)) = *reinterpret_cast<const uint4*>(stg + c * 16);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(out_empty(slot));
     }
   } else if (warp == kTALoaderWarp) {
     // =========================================== loader: bulk copies ===========================================
@@ -434,22 +493,28 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
         if (kb == 0) { mbar_wait(q_full(s), n_q[s] & 1); ++n_q[s]; TA_TR(3, 30 + s); }
         if (p.shared_mode ? (j.load && s == 0) : true) { mbar_wait(kv_full((int)st), (ri / nst) & 1); TA_TR(3, 32); }
         tc_fence_after();
-        if (leader) {
-          const uint32_t tS = tmem_base + (uint32_t)(s * 256);
-          const uint32_t qlo = q16[s], klo = kv16 + st * stage16;
-          uint32_t acc = 0;
+        // everything but the tcgen05 instructions themselves runs on the whole warp, so the operands stay in uniform
+        // registers and the MMAs issue back to back (a leader-only region makes them thread-private: ~30 extra
+        // instructions per MMA)
+        const uint32_t tS = tmem_base + (uint32_t)(s * 256);
+        const uint32_t qlo = q16[s], klo = kv16 + st * stage16;
 #pragma unroll
-          for (int kc = 0; kc < Cfg::MAIN; ++kc) {
+        for (int kc = 0; kc < Cfg::MAIN; ++kc) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              umma_bf16<1>(tS, desc(qlo + kc * q_chunk16 + ks * 2, kHiSw128), desc(klo + kc * k_chunk16 + ks * 2, kHiSw128), idesc_s, acc);
-              acc = 1;
-            }
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t da = desc(qlo + kc * q_chunk16 + ks * 2, kHiSw128), db = desc(klo + kc * k_chunk16 + ks * 2, kHiSw128);
+            if (leader && !(p.exp_flags & 32)) umma_bf16<1>(tS, da, db, idesc_s, (kc | ks) ? 1u : 0u);
           }
-          if (Cfg::TAIL)
-            umma_bf16<1>(tS, desc((qlo + Cfg::MAIN * q_chunk16) | lbo_tail_k, kHiTailK), desc((klo + Cfg::MAIN * k_chunk16) | lbo_tail_k, kHiTailK), idesc_s, acc);
+        }
+        if (Cfg::TAIL) {
+          const uint64_t da = desc((qlo + Cfg::MAIN * q_chunk16) | lbo_tail_k, kHiTailK);
+          const uint64_t db = desc((klo + Cfg::MAIN * k_chunk16) | lbo_tail_k, kHiTailK);
+          if (leader && !(p.exp_flags & (4 | 32))) umma_bf16<1>(tS, da, db, idesc_s, 1u);
+        }
+        const bool last_s = kb == j.nkb[s] - 1;
+        if (leader) {
           umma_commit<1>(s_full(s));
-          if (kb == j.nkb[s] - 1) umma_commit<1>(q_empty(s));   // the Q buffer may be refilled for the next job
+          if (last_s) umma_commit<1>(q_empty(s));   // the Q buffer may be refilled for the next job
         }
         __syncwarp();
         TA_TR(3, 34 + s);
@@ -461,22 +526,38 @@ __global__ void __launch_bounds__(kTAThreads, 1) attn_tiles_kernel(const TileAtt
         mbar_wait(p_full(s), n_p[s] & 1); ++n_p[s];
         tc_fence_after();
         TA_TR(3, 36 + s);
-        if (leader) {
-          const uint32_t tS = tmem_base + (uint32_t)(s * 256), tO = tS + 128;
-          const uint32_t vlo = (kv16 + st * stage16 + kv_slot16) | lbo_v;
-          const uint32_t vtl = (kv16 + st * stage16 + kv_slot16 + Cfg::MAIN * k_chunk16) | lbo_tail_mn;
+        const uint32_t tS = tmem_base + (uint32_t)(s * 256), tO = tS + 128;
+        const uint32_t vlo = (kv16 + st * stage16 + kv_slot16) | lbo_v;
+        const uint32_t vtl = (kv16 + st * stage16 + kv_slot16 + Cfg::MAIN * k_chunk16) | lbo_tail_mn;
+        const uint32_t acc0 = kb > 0 ? 1u : 0u;
+        if (steps == 8 && p.exp_flags == 0) {
+          // full key tile (the common case): straight-line issue, every operand a compile-time offset from a uniform
+          // base - the tensor pipe, not this thread's instruction stream, must pace the PV product
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            if (i < steps) {
-              const uint32_t accu = (kb > 0 || i > 0) ? 1u : 0u;
-              umma_bf16_ts(tO, tS + (uint32_t)(i * 8), desc(vlo + i * (2048 >> 4), kHiSw128), idesc_om, accu);
-              if (Cfg::TAIL) umma_bf16_ts(tO + NMAIN, tS + (uint32_t)(i * 8), desc(vtl + i * (512 >> 4), kHiTailMN), idesc_ot, accu);
+            const uint64_t dm = desc(vlo + i * (2048 >> 4), kHiSw128), dt = desc(vtl + i * (512 >> 4), kHiTailMN);
+            if (leader) {
+              umma_bf16_ts(tO, tS + (uint32_t)(i * 8), dm, idesc_om, i == 0 ? acc0 : 1u);
+              if (Cfg::TAIL) umma_bf16_ts(tO + NMAIN, tS + (uint32_t)(i * 8), dt, idesc_ot, i == 0 ? acc0 : 1u);
             }
           }
-          // the stage is free once its last reader is done: slot 1 (or slot 0 alone) in shared mode, the slot itself otherwise
-          const bool last_reader = p.shared_mode ? (j.release && (s == 1 || !j.act[1])) : true;
+        } else {
+#pragma unroll 1
+          for (int i = 0; i < steps; ++i) {
+            const uint32_t accu = (kb > 0 || i > 0) ? 1u : 0u;
+            const uint64_t dm = desc(vlo + i * (2048 >> 4), kHiSw128), dt = desc(vtl + i * (512 >> 4), kHiTailMN);
+            if (leader && !(p.exp_flags & 2)) {
+              umma_bf16_ts(tO, tS + (uint32_t)(i * 8), dm, idesc_om, accu);
+              if (Cfg::TAIL && !(p.exp_flags & 1)) umma_bf16_ts(tO + NMAIN, tS + (uint32_t)(i * 8), dt, idesc_ot, accu);
+            }
+          }
+        }
+        // the stage is free once its last reader is done: slot 1 (or slot 0 alone) in shared mode, the slot itself otherwise
+        const bool last_reader = p.shared_mode ? (j.release && (s == 1 || !j.act[1])) : true;
+        const bool last_pv = kb == j.nkb[s] - 1;
+        if (leader) {
           if (last_reader) umma_commit<1>(kv_empty((int)st));
-          if (kb == j.nkb[s] - 1) umma_commit<1>(o_full(s));
+          if (last_pv) umma_commit<1>(o_full(s));
         }
         __syncwarp();
         TA_TR(3, 38 + s);
@@ -520,12 +601,15 @@ static int attn_tiles_launch(TileAttnParams& p, cudaStream_t stream) {
   p.kv_tile_bytes = p.BK * Cfg::ROW_BYTES;
   p.kv_slot_bytes = up1k(p.kv_tile_bytes);
   p.off_kv = 2 * p.q_slot_bytes;
-  const int budget = 227 * 1024 - p.off_kv - 1024;
+  int out_bytes = 2 * (128 * D * 2 + 128 * 8);   // output staging tile + row pointers, per slot
+  if ((227 * 1024 - p.off_kv - out_bytes - 1024) / (2 * p.kv_slot_bytes) < 2) out_bytes = 0;   // large head_dim: direct stores
+  const int budget = 227 * 1024 - p.off_kv - out_bytes - 1024;
   int nst = budget / (2 * p.kv_slot_bytes);
   if (nst > kTAMaxStages) nst = kTAMaxStages;
   if (nst < 2) { set_error("osb_attn_tiles: key tiles of %d rows do not fit twice in shared memory", p.BK); return OSB_ERR_UNSUPPORTED; }
   p.nst = nst;
-  p.off_bar = p.off_kv + nst * 2 * p.kv_slot_bytes;
+  p.off_out = out_bytes ? p.off_kv + nst * 2 * p.kv_slot_bytes : -1;
+  p.off_bar = p.off_kv + nst * 2 * p.kv_slot_bytes + out_bytes;
   const int smem = p.off_bar + 256;
   p.shared_mode = (p.qmap.G == 1 && p.qmap.tps >= 2) ? 1 : 0;
   if (p.shared_mode) {
@@ -602,6 +686,7 @@ extern "C" int osb_attn_tiles(const osb_attn_tiles_args* a, void* stream) {
   p.out = static_cast<__nv_bfloat16*>(a->out);
   p.out_ld = a->out_ld;
   p.scale_log2 = a->softmax_scale * 1.4426950408889634f;
+  { const char* e = getenv("OSB_TA_EXP"); p.exp_flags = e ? atoi(e) : 0; }
   {
     const int64_t out_rows = a->num_seqs * m.L;
     const int rc = make_row_scatter(&p.out_sc, a->out_scatter, out_rows, "osb_attn_tiles");

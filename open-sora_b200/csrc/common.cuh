@@ -419,6 +419,14 @@ __device__ __forceinline__ void scatter_row(const RowScatter& sc, int64_t row, i
     const uint32_t p = j / jc;
     peer = (int)p;
     dst_row = ((int64_t)b * sc.P * sc.I + (int64_t)sc.rank * sc.I + i) * jc + (j - p * jc);
+  } else if (sc.mode == 3) {          // transpose in place of the rank: [B, I, J] -> [B, J, I]
+    peer = sc.rank;
+    dst_row = ((int64_t)b * sc.J + j) * sc.I + i;
+  } else if (sc.mode == 4) {          // split J like mode 1, destination transposed: rank p holds [B, J/P, P*I]
+    const uint32_t jc = (uint32_t)sc.J / (uint32_t)sc.P;
+    const uint32_t p = j / jc;
+    peer = (int)p;
+    dst_row = ((int64_t)b * jc + (j - p * jc)) * ((int64_t)sc.P * sc.I) + (int64_t)sc.rank * sc.I + i;
   } else {
     const uint32_t ic = (uint32_t)sc.I / (uint32_t)sc.P;
     const uint32_t p = i / ic;

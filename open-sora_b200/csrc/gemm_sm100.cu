@@ -26,6 +26,7 @@ constexpr int kStagePitch = 36;                       // floats per staged row: 
 constexpr int kEpiStageBytes = kEpiWarps * 32 * kStagePitch * 4;  // one [32 x 32] fp32 tile per epilogue warp
 constexpr int kResChunkBytes = kBlockM * 64 * 2;      // residual ring slot: [128 rows x 64 cols] bf16, SW128
 constexpr int kBarBytes = 256;
+constexpr int kRopeSmemBytes = 18 * 1024;             // head-tile epilogue: RoPE table of up to 64 positions x 72 dims in smem
 constexpr int kSmemTotal = 227 * 1024;
 
 struct GemmEpilogueParams {
@@ -57,7 +58,8 @@ struct HeadTileParams {
   const float* sin;
   // aligned fast path: every CTA's 128 accumulator rows ARE one head tile (row r of the CTA = row r of the tile), so the
   // epilogue builds the tile image in shared memory and writes it with one bulk store per head.
-  //   1: contiguous sequences with tile_rows == 128 and L % 128 == 0 (tile = CTA's row block);
+  //   1: contiguous sequences with tile_rows == 128 and L % 128 == 0, or G = 128 / L short sequences packed per tile
+  //      (tile = CTA's row block; the temporal case when the producer wrote the rows transposed to [B, S, T]);
   //   2: temporal view: the A operand is loaded through a strided TMA view [k][t][s][b] whose box is (64, T, G):
   //      the M-tile of (batch b, sequence group sg) holds rows g*T + t - exactly the packed temporal attention tile.
   int32_t fast;
@@ -87,7 +89,8 @@ struct GemmCfg {
   static constexpr int RES_STAGES = kRes ? (BLOCK_N <= 128 ? 4 : 3) : 0;
   static constexpr int RES_BYTES = RES_STAGES * kResChunkBytes;
   // epilogue staging: per-warp fp32 tiles, or (head tiles) the bf16 images of the two head tiles a CTA produces
-  static constexpr int EPI_BYTES = kHT ? 2 * kBlockM * (((BLOCK_N / 2) + 15) / 16 * 16) * 2 : kEpiStageBytes;
+  static constexpr int ROPE_BYTES = kHT ? kRopeSmemBytes : 0;   // cos / sin rows of a short sequence, staged once per CTA
+  static constexpr int EPI_BYTES = kHT ? 2 * kBlockM * (((BLOCK_N / 2) + 15) / 16 * 16) * 2 + ROPE_BYTES : kEpiStageBytes;
   static constexpr int FIXED_BYTES = RES_BYTES + kBarBytes + EPI_BYTES + 1024;  // +1024 alignment slack
   static constexpr int STAGES_RAW = (kSmemTotal - FIXED_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -313,6 +316,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* stage_h = smem_raw + (stage_base - smem_u32(smem_raw)) + hh * (kBlockM * HT::ROW_BYTES);
     const bool store_leader = (q == 0 && lane == 0);       // issues this head's bulk stores
     const int chunk_bytes = ht.map.TR * 128;
+    // RoPE tables: in the aligned temporal path a warp's 32 rows are 32 DIFFERENT positions, so table reads from global
+    // memory would touch 32 lines per instruction (18 instructions per row): short tables are staged in shared memory once
+    // (row pitch D*2 bytes: conflict-free 16-byte reads)
+    float* rope_s = reinterpret_cast<float*>(smem_raw + (stage_base - smem_u32(smem_raw)) + 2 * (kBlockM * HT::ROW_BYTES));
+    const bool rope_smem = ht.rope_mask != 0 && ht.map.L * D * 4 <= kRopeSmemBytes;
+    if (rope_smem) {
+      const int n = ht.map.L * (D / 2);
+      for (int i = (e * 32 + lane); i < n; i += kEpiWarps * 32) { rope_s[i] = __ldg(ht.cos + i); rope_s[n + i] = __ldg(ht.sin + i); }
+      asm volatile("bar.sync 3, %0;" ::"r"(kEpiWarps * 32) : "memory");
+    }
     int as = 0;
     uint32_t aphase = 0;
     for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -350,7 +363,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tile_i = (uint32_t)(m_blk * kCta + cta_rank);
         r = r_loc;
         row_ok = r_loc < ht.a_rows && tile_i < (uint32_t)ht.tiles_total;
-        pos = ht.fast == 2 ? (uint32_t)r_loc % (uint32_t)ht.map.L
+        pos = ht.map.G > 1 ? (uint32_t)r_loc % (uint32_t)ht.map.L
                            : (tile_i % (uint32_t)ht.map.tps) * (uint32_t)ht.map.TR + (uint32_t)r_loc;
       } else {   // (32-bit arithmetic: the host checks M < 2^31)
         uint32_t seq;
@@ -412,11 +425,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
         if ((ht.rope_mask >> kind) & 1u) {
-          const float4* cr = reinterpret_cast<const float4*>(ht.cos + (int64_t)pos * (D / 2));
-          const float4* sr = reinterpret_cast<const float4*>(ht.sin + (int64_t)pos * (D / 2));
+          const float4* cr = rope_smem ? reinterpret_cast<const float4*>(rope_s + pos * (D / 2))
+                                       : reinterpret_cast<const float4*>(ht.cos + (int64_t)pos * (D / 2));
+          const float4* sr = rope_smem ? reinterpret_cast<const float4*>(rope_s + ht.map.L * (D / 2) + pos * (D / 2))
+                                       : reinterpret_cast<const float4*>(ht.sin + (int64_t)pos * (D / 2));
 #pragma unroll
           for (int u = 0; u < HT::U; ++u) {
-            const float4 c4 = __ldg(cr + u), s4 = __ldg(sr + u);
+            const float4 c4 = cr[u], s4 = sr[u];
             const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -652,7 +667,7 @@ static int launch_gemm_ht(const osb_gemm_args& a, HeadTileParams ht, bool allow_
   ht.fast = 0;
   ht.a_rows = kBlockM;
   if (allow_fast && ht_fast_enabled()) {
-    if (m.mode == 0 && m.G == 1 && m.TR == kBlockM && m.L % kBlockM == 0) ht.fast = 1;
+    if (m.mode == 0 && m.TR == kBlockM && (m.G == 1 ? m.L % kBlockM == 0 : m.G * m.L == kBlockM)) ht.fast = 1;
     else if (m.mode == 1 && m.tps == 1 && m.S % m.G == 0 && m.G * m.L <= m.TR && (int64_t)m.L * m.G <= kBlockM) ht.fast = 2;
   }
   int64_t m_rows = a.M;

@@ -19,13 +19,20 @@ import torch.distributed as dist
 def scatter_dest(mode: int, P: int, rank: int, I: int, J: int, row: int) -> tuple[int, int]:
     """Host mirror of the device routing (`scatter_row`, open-sora_b200/csrc/common.cuh; include/osb200.h `osb_scatter`):
     row `row` of a [B, I, J] producer on `rank` -> (destination rank, row in its buffer).  mode 1 splits J
-    ([B, Tl, S] -> [B, T, S/P]), mode 2 splits I ([B, T, Sl] -> [B, T/P, S])."""
+    ([B, Tl, S] -> [B, T, S/P]), mode 2 splits I ([B, T, Sl] -> [B, T/P, S]), mode 3 transposes locally
+    ([B, T, S] -> [B, S, T]), mode 4 = mode 1 with the destination transposed ([B, Tl, S] -> [B, S/P, T])."""
     b, rem = divmod(row, I * J)
     i, j = divmod(rem, J)
     if mode == 1:
         jc = J // P
         p = j // jc
         return p, (b * P * I + rank * I + i) * jc + (j - p * jc)
+    if mode == 3:
+        return rank, (b * J + j) * I + i
+    if mode == 4:
+        jc = J // P
+        p = j // jc
+        return p, (b * jc + (j - p * jc)) * (P * I) + rank * I + i
     ic = I // P
     p = i // ic
     return p, (b * ic + (i - p * ic)) * (P * J) + rank * J + j

@@ -438,7 +438,14 @@ class STDiT3(nn.Module):
         if use_tiles:
             Sl = S // P   # temporal attention runs on this rank's S/P columns of every frame
             ws["sp_t"] = self._tiles(osb, ("spatial", B, Tl, S), R, osb.tile_map(0, S), 3, dev)
-            ws["tm_t"] = self._tiles(osb, ("temporal", B, T, Sl), B * T * Sl, osb.tile_map(1, T, Sl, T), 3, dev)
+            # temporal attention tiles.  Default: LN+modulate writes its rows transposed to [B, S, T] (a free row
+            # permutation of its stores), so a temporal sequence is a contiguous row block for the QKV GEMM (tile map mode 0)
+            # and only the attention OUTPUT is addressed frame-major (`tm_out`, mode 1).  When the rows arrive frame-major
+            # (NCCL all-to-all exchange) the GEMM reads them through a strided TMA view instead (mode 1 map).
+            ws["tm_out"] = osb.tile_map(1, T, Sl, T)
+            ws["tm_t"] = self._tiles(osb, ("temporal", B, T, Sl), B * T * Sl, osb.tile_map(0, T), 3, dev)
+            ws["tm_t_strided"] = (lambda: self._tiles(osb, ("temporal-fm", B, T, Sl), B * T * Sl, ws["tm_out"], 3, dev))
+            ws["xm_t"] = torch.empty(R, C, dtype=bf, device=dev) if P == 1 else None
             ws["q_t"] = self._tiles(osb, ("crossq", B, N), R, osb.tile_map(0, N, pack=False), 1, dev)
         else:
             ws["qkv"] = torch.empty(R, 3 * C, dtype=bf, device=dev)
@@ -494,17 +501,27 @@ class STDiT3(nn.Module):
             # owns its S-column, the attention epilogue stores every output row into the ao buffer of the rank that owns
             # its frame; one barrier kernel after each producer.  Rows stay B*T*S/P on both sides.
             Sl = S // (T // Tl)
-            xt, xt_ptrs = peer.buffer("xt", B * T * Sl, C)
+            xt, xt_ptrs = peer.buffer("xt", B * Sl * T, C)
             ar, ar_ptrs = peer.buffer("ao", B * N, C)
             osb.ln_modulate(xs, m[:, 0], m[:, 1], group_rows=group_rows, mod_index=mod_index,
-                            scatter=peer.scatter(1, Tl, S, xt_ptrs))
+                            scatter=peer.scatter(4, Tl, S, xt_ptrs))     # -> [B, S/P, T] on the rank that owns the column
             peer.barrier()
             tt = ws["tm_t"]
             osb.gemm_head_tiles(xt, a.qkv.weight, a.qkv.bias, tt, nkinds=3, norm_w=(qn, kn, None), rope=(cos, sin),
                                 rope_kinds=0b011)
-            osb.attn_tiles(tt, tt, None, Lk=T, num_seqs=B * Sl, out_scatter=peer.scatter(2, T, Sl, ar_ptrs), out_ld=C)
+            osb.attn_tiles(tt, tt, None, Lk=T, num_seqs=B * Sl, out_map=ws["tm_out"],
+                           out_scatter=peer.scatter(2, T, Sl, ar_ptrs), out_ld=C)
             peer.barrier()
             ao = ar
+        elif blk.temporal and tiles and sp is None:
+            # single GPU: LN+modulate stores its rows transposed ([B, T, S] -> [B, S, T]) so temporal sequences are
+            # contiguous row blocks; the attention output comes back frame-major
+            xm_t, tt = ws["xm_t"], ws["tm_t"]
+            osb.ln_modulate(xs, m[:, 0], m[:, 1], group_rows=group_rows, mod_index=mod_index,
+                            scatter=osb.make_scatter(3, 1, 0, T, S, [xm_t]))
+            osb.gemm_head_tiles(xm_t, a.qkv.weight, a.qkv.bias, tt, nkinds=3, norm_w=(qn, kn, None), rope=(cos, sin),
+                                rope_kinds=0b011)
+            osb.attn_tiles(tt, tt, ao, Lk=T, num_seqs=B * S, out_map=ws["tm_out"])
         elif blk.temporal:
             osb.ln_modulate(xs, m[:, 0], m[:, 1], group_rows=group_rows, mod_index=mod_index, out=xm_buf)
             if sp is not None:
@@ -518,7 +535,7 @@ class STDiT3(nn.Module):
                 Sl, xt = S, xm_buf
             ao_t = ao if sp is None else torch.empty_like(ao)
             if tiles:
-                tt = ws["tm_t"]
+                tt = ws["tm_t_strided"]()
                 osb.gemm_head_tiles(xt, a.qkv.weight, a.qkv.bias, tt, nkinds=3, norm_w=(qn, kn, None), rope=(cos, sin),
                                     rope_kinds=0b011)
                 osb.attn_tiles(tt, tt, ao_t, Lk=T, num_seqs=B * Sl)

@@ -261,8 +261,8 @@ class CommBarrierArgs(C.Structure):
 def make_scatter(mode: int, P: int, rank: int, I: int, J: int, peer_ptrs) -> Scatter:
     sc = Scatter()
     sc.mode, sc.P, sc.rank, sc.I, sc.J = mode, P, rank, I, J
-    for i, ptr in enumerate(peer_ptrs):
-        sc.peer[i] = int(ptr)
+    for i, ptr in enumerate(peer_ptrs):   # raw (peer-mapped) device pointers, or local tensors
+        sc.peer[i] = int(ptr) if isinstance(ptr, int) else ptr.data_ptr()
     return sc
 
 
@@ -478,16 +478,20 @@ def gemm_head_tiles(a, w, bias, tiles: HeadTiles, *, nkinds: int, norm_w=(), rop
 
 def attn_tiles(q: HeadTiles, kv: HeadTiles, out, *, q_kind: int = 0, k_kind: int = 1, v_kind: int = 2, Lk: int,
                num_seqs: int, kv_lens=None, softmax_scale: float | None = None, out_scatter: Scatter | None = None,
-               out_ld: int | None = None):
+               out_ld: int | None = None, out_map: TileMap | None = None):
     """out = softmax(q k^T * scale) v per (sequence, head) over head tiles (osb_attn_tiles).  Self-attention: q and kv
-    are the same buffer (kinds 0, 1, 2); cross-attention: kv holds the text keys / values (`keys_only` map)."""
+    are the same buffer (kinds 0, 1, 2); cross-attention: kv holds the text keys / values (`keys_only` map).
+    `out_map`: the token order of `out` when it differs from the order the q tiles were written from (temporal attention:
+    tiles from the transposed [B, S, T] stream (mode 0), output rows frame-major (mode 1))."""
     import torch
 
     _need(out, torch.bfloat16, "out"); _need(kv_lens, torch.int32, "kv_lens")
     assert (out is None) != (out_scatter is None), "exactly one of out / out_scatter"
     a = AttnTilesArgs()
     a.q_tiles, a.k_tiles, a.v_tiles = q.kind_ptr(q_kind), kv.kind_ptr(k_kind), kv.kind_ptr(v_kind)
-    a.q_head_stride, a.kv_head_stride, a.q_map = q.head_stride, kv.head_stride, q.map
+    if out_map is not None:   # output rows in another order than the rows the tiles were written from (same tiling)
+        assert out_map.key()[4:] == q.map.key()[4:] and out_map.L == q.map.L
+    a.q_head_stride, a.kv_head_stride, a.q_map = q.head_stride, kv.head_stride, (out_map if out_map is not None else q.map)
     a.kv_tile_rows = kv.map.tile_rows
     a.kv_tiles_per_set = kv.map.tps
     a.Lk, a.num_heads, a.head_dim = Lk, q.heads, q.head_dim

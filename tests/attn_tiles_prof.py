@@ -58,6 +58,10 @@ def timed(fn):
 cases = [
     ("qkv gemm -> tiles (spatial)", lambda: osb.gemm_head_tiles(x, wqkv, bqkv, sp_t, nkinds=3, norm_w=(nw, nw, None)), 2.0 * N * 3 * C * C),
     ("qkv gemm -> tiles (temporal)", lambda: osb.gemm_head_tiles(x, wqkv, bqkv, tm_t, nkinds=3, norm_w=(nw, nw, None), rope=(cos, sin), rope_kinds=3), 2.0 * N * 3 * C * C),
+    ("qkv gemm -> tiles (temporal, no rope)", lambda: osb.gemm_head_tiles(x, wqkv, bqkv, tm_t, nkinds=3, norm_w=(nw, nw, None)), 2.0 * N * 3 * C * C),
+    ("qkv gemm -> tiles (temporal, no rope, no norm)", lambda: osb.gemm_head_tiles(x, wqkv, bqkv, tm_t, nkinds=3), 2.0 * N * 3 * C * C),
+    ("qkv gemm -> tiles (temporal, general)", lambda: osb.gemm_head_tiles(x, wqkv, bqkv, tm_t, nkinds=3, norm_w=(nw, nw, None), rope=(cos, sin), rope_kinds=3, general=True), 2.0 * N * 3 * C * C),
+    ("qkv gemm -> tiles (spatial, no norm)", lambda: osb.gemm_head_tiles(x, wqkv, bqkv, sp_t, nkinds=3), 2.0 * N * 3 * C * C),
     ("qkv gemm plain", lambda: osb.gemm(x, wqkv, bqkv, out=qkv), 2.0 * N * 3 * C * C),
     ("q gemm -> tiles (cross)", lambda: osb.gemm_head_tiles(x, wq, None, q_t, nkinds=1), 2.0 * N * C * C),
     ("q gemm plain", lambda: osb.gemm(x, wq, out=qc), 2.0 * N * C * C),

@@ -75,7 +75,25 @@ def _groups(rows, group_rows, mod_index, device):
     return g
 
 
-def ln_modulate(x, shift, scale, *, group_rows: int, mod_index=None, eps: float = 1e-6, out=None):
+class Scatter:
+    def __init__(self, mode, P, rank, I, J, peers):
+        self.mode, self.P, self.rank, self.I, self.J, self.peers = mode, P, rank, I, J, peers
+
+
+def make_scatter(mode, P, rank, I, J, peer_bufs):
+    """The double routes rows into torch tensors (`peer_bufs`) instead of raw pointers; only what one process can do on its
+    own is supported: P == 1 (mode 3, the local transpose)."""
+    return Scatter(mode, P, rank, I, J, peer_bufs)
+
+
+def ln_modulate(x, shift, scale, *, group_rows: int, mod_index=None, eps: float = 1e-6, out=None, scatter=None):
+    if scatter is not None:
+        assert scatter.mode == 3 and scatter.P == 1, "the CPU double only routes the local transpose"
+        y = ln_modulate(x, shift, scale, group_rows=group_rows, mod_index=mod_index, eps=eps)
+        I, J = scatter.I, scatter.J
+        B = x.shape[0] // (I * J)
+        scatter.peers[0].copy_(y.view(B, I, J, -1).transpose(1, 2).reshape(x.shape[0], -1))
+        return None
     _need(x, torch.bfloat16, "x"); _need(shift, torch.float32, "shift"); _need(scale, torch.float32, "scale")
     _need(mod_index, torch.int32, "mod_index")
     assert x.dim() == 2 and x.is_contiguous()
@@ -366,11 +384,18 @@ def gemm_head_tiles(a, w, bias, tiles, *, nkinds, norm_w=(), rope=None, rope_kin
 
 
 def attn_tiles(q, kv, out, *, q_kind=0, k_kind=1, v_kind=2, Lk, num_seqs, kv_lens=None, softmax_scale=None,
-               out_scatter=None, out_ld=None):
+               out_scatter=None, out_ld=None, out_map=None):
     H, D = q.heads, q.head_dim
     m = q.map
     scale = softmax_scale if softmax_scale is not None else D ** -0.5
-    seq_q, _ = _seq_pos(m, q.rows, out.device)
+    seq_q, pos_q = _seq_pos(m, q.rows, out.device)
+    out_rows = None
+    if out_map is not None:   # output rows in another token order: (seq, pos) -> row of `out`
+        assert out_map.key()[4:] == m.key()[4:] and out_map.L == m.L
+        so, po = _seq_pos(out_map, q.rows, out.device)
+        inv = torch.empty(q.rows, dtype=torch.long, device=out.device)
+        inv[so * m.L + po] = torch.arange(q.rows, device=out.device)
+        out_rows = inv[seq_q * m.L + pos_q]
     seq_k, pos_k = _seq_pos(kv.map, kv.rows, out.device)
     assert int(seq_q.max()) + 1 == num_seqs
     for s in range(num_seqs):
@@ -378,14 +403,15 @@ def attn_tiles(q, kv, out, *, q_kind=0, k_kind=1, v_kind=2, Lk, num_seqs, kv_len
         rk = (seq_k == s).nonzero().flatten()
         rk = rk[pos_k[rk].argsort()]
         n = Lk if kv_lens is None else min(int(kv_lens[s]), Lk)
+        ro = rq if out_rows is None else out_rows[rq]
         if n <= 0:
-            out[rq] = 0
+            out[ro] = 0
             continue
         rk = rk[:n]
         qq = q.dense[q_kind][rq].float().view(-1, H, D).permute(1, 0, 2)
         kk = kv.dense[k_kind][rk].float().view(-1, H, D).permute(1, 0, 2)
         vv = kv.dense[v_kind][rk].float().view(-1, H, D).permute(1, 0, 2)
         pr = torch.softmax(qq @ kk.transpose(-1, -2) * scale, dim=-1).to(torch.bfloat16).float()
-        out[rq] = (pr @ vv).permute(1, 0, 2).reshape(len(rq), H * D).to(torch.bfloat16)
+        out[ro] = (pr @ vv).permute(1, 0, 2).reshape(len(rq), H * D).to(torch.bfloat16)
     _count("attn_tiles", (num_seqs, m.L, Lk, H, D))
     return out

@@ -32,7 +32,7 @@ osb.gemm_head_tiles(x, wqkv, None, tm_t, nkinds=3)
 osb.gemm_head_tiles(x, wq, None, q_t, nkinds=1)
 osb.gemm_head_tiles(y, wkv, None, kv_t, nkinds=2)
 
-NAMES = {10: "s_full", 11: "S in regs", 12: "max done", 13: "P stored+arrived", 14: "o_full", 15: "O in regs", 16: "out stored",
+NAMES = {10: "s_full", 11: "S in regs", 12: "max done", 13: "P stored+arrived", 14: "o_full", 15: "O in regs", 16: "out stored", 17: "stage free", 18: "staged",
          20: "Q0 load", 21: "Q1 load", 22: "KV load", 30: "q_full 0", 31: "q_full 1", 32: "kv_full", 34: "S issued 0",
          35: "S issued 1", 36: "p_full 0", 37: "p_full 1", 38: "PV issued 0", 39: "PV issued 1"}
 ROLE = ["softmax0", "softmax1", "loader", "issuer"]

@@ -64,7 +64,7 @@ def read_tiles(tiles, kind):
     return out.view(torch.bfloat16)
 
 
-def _self_case(mode, B, T, S, H, D, seed=0, general=False):
+def _self_case(mode, B, T, S, H, D, seed=0, general=False, transposed=False):
     """One STDiT3-style self-attention: tokens frame-major [B, T, S]; mode 0 attends over S, mode 1 over T (with RoPE)."""
     import osb200 as osb
 
@@ -82,12 +82,17 @@ def _self_case(mode, B, T, S, H, D, seed=0, general=False):
     ang = torch.arange(L).float()[:, None] * inv[None]
     cos, sin = ang.cos().contiguous().to(dev), ang.sin().contiguous().to(dev)
     tm = osb.tile_map(0, S) if mode == 0 else osb.tile_map(1, T, S, T)
+    x_in, out_map = x, None
+    if transposed:   # temporal sequences as contiguous row blocks ([B, S, T] stream), output still frame-major
+        assert mode == 1
+        x_in = x.view(B, T, S, C).transpose(1, 2).reshape(R, C).contiguous()
+        tm, out_map = osb.tile_map(0, T), tm
     tiles = osb.HeadTiles(R, tm, 3, H, D, dev)
-    osb.gemm_head_tiles(x, w, bias, tiles, nkinds=3, norm_w=(qn, kn, None), rope=(cos, sin) if mode == 1 else None,
+    osb.gemm_head_tiles(x_in, w, bias, tiles, nkinds=3, norm_w=(qn, kn, None), rope=(cos, sin) if mode == 1 else None,
                         rope_kinds=0b011, general=general)
     out = torch.full((R, C), float("nan"), dtype=torch.bfloat16, device=dev)
     nseq = B * T if mode == 0 else B * S
-    osb.attn_tiles(tiles, tiles, out, Lk=L, num_seqs=nseq)
+    osb.attn_tiles(tiles, tiles, out, Lk=L, num_seqs=nseq, out_map=out_map)
     torch.cuda.synchronize()
 
     # fp32 restatement
@@ -105,6 +110,8 @@ def _self_case(mode, B, T, S, H, D, seed=0, general=False):
         return t.reshape(R, C)
     for kind, ref in enumerate((q, k, v)):
         got = read_tiles(tiles, kind).float()
+        if transposed:
+            got = got.view(B, S, T, C).transpose(1, 2).reshape(R, C)
         e = rel_l2(got, back(ref))
         assert e < 2.5e-3, (kind, e)
     # attention on the bf16-rounded operands the kernel sees
@@ -242,3 +249,74 @@ def test_matches_register_path_kernel():
     new = torch.empty_like(old)
     osb.attn_tiles(tiles, tiles, new, Lk=S, num_seqs=B * T)
     assert rel_l2(new.float(), old.float()) < 6e-3
+
+
+@pytest.mark.parametrize("B,T,S,H", [(1, 64, 8, 4), (2, 64, 6, 2), (1, 32, 20, 2), (3, 16, 5, 2), (1, 17, 10, 2), (1, 100, 6, 2)])
+def test_transposed_temporal_stream(B, T, S, H):
+    """Temporal attention from a [B, S, T]-ordered token stream (what LN+modulate writes with osb_scatter mode 3): the QKV
+    GEMM sees contiguous sequences (tile map mode 0, aligned epilogue when G*T == 128), the output rows are frame-major."""
+    _self_case(1, B, T, S, H, 72, transposed=True)
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
+def test_scatter_routing_on_one_gpu(mode):
+    """osb_scatter row routing with the P 'ranks' simulated by P local buffers: every rank's LN+modulate call stores its
+    rows into the buffer of the rank that consumes them; the buffers must equal the reference's all_to_all result
+    (communications.py:8-18), or its transposed forms (modes 3, 4)."""
+    import osb200 as osb
+
+    dev = _dev()
+    P = 1 if mode == 3 else 4
+    B, T, S, C = 2, 8, 12, 64
+    g = torch.Generator().manual_seed(9)
+    full = torch.randn(B, T, S, C, generator=g).to(torch.bfloat16).to(dev)
+    zeros = torch.zeros(1, C, dtype=torch.float32, device=dev)
+    ref = torch.nn.functional.layer_norm(full.float(), (C,), eps=1e-6)
+    Tl, Sl = T // P, S // P
+    if mode in (1, 4):      # producers hold [B, Tl, S] (T-sharded), rank p ends up with every frame of its S/P columns
+        bufs = [torch.full((B * T * Sl, C), float("nan"), dtype=torch.bfloat16, device=dev) for _ in range(P)]
+        for r in range(P):
+            x = full[:, r * Tl:(r + 1) * Tl].reshape(B * Tl * S, C).contiguous()
+            osb.ln_modulate(x, zeros, zeros, group_rows=x.shape[0], scatter=osb.make_scatter(mode, P, r, Tl, S, bufs))
+        for p in range(P):
+            want = ref[:, :, p * Sl:(p + 1) * Sl]
+            want = want if mode == 1 else want.transpose(1, 2)
+            assert rel_l2(bufs[p].float().view(want.shape), want) < 3e-3
+    elif mode == 2:         # producers hold [B, T, Sl] (S-sharded), rank p ends up with its T/P frames, all columns
+        bufs = [torch.full((B * Tl * S, C), float("nan"), dtype=torch.bfloat16, device=dev) for _ in range(P)]
+        for r in range(P):
+            x = full[:, :, r * Sl:(r + 1) * Sl].reshape(B * T * Sl, C).contiguous()
+            osb.ln_modulate(x, zeros, zeros, group_rows=x.shape[0], scatter=osb.make_scatter(2, P, r, T, Sl, bufs))
+        for p in range(P):
+            assert rel_l2(bufs[p].float().view(B, Tl, S, C), ref[:, p * Tl:(p + 1) * Tl]) < 3e-3
+    else:                   # local transpose [B, T, S] -> [B, S, T]
+        buf = torch.full((B * S * T, C), float("nan"), dtype=torch.bfloat16, device=dev)
+        osb.ln_modulate(full.reshape(B * T * S, C), zeros, zeros, group_rows=B * T * S, scatter=osb.make_scatter(3, 1, 0, T, S, [buf]))
+        assert rel_l2(buf.float().view(B, S, T, C), ref.transpose(1, 2)) < 3e-3
+
+
+def test_attention_output_scatter_on_one_gpu():
+    """The attention kernel's output rows routed by osb_scatter mode 2 (S-sharded temporal attention -> T-sharded token
+    stream), 2 simulated ranks on one GPU: each 'rank' runs temporal attention on its S/P columns of the transposed stream
+    and stores into the rank that owns the frame."""
+    import osb200 as osb
+
+    dev = _dev()
+    P, B, T, S, H, D = 2, 1, 64, 8, 2, 72
+    C, Sl, Tl = H * D, S // P, T // P
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(B, T, S, C, generator=g).to(torch.bfloat16).to(dev)
+    w = (torch.randn(3 * C, C, generator=g) / math.sqrt(C)).to(torch.bfloat16).to(dev)
+    bufs = [torch.full((B * Tl * S, C), float("nan"), dtype=torch.bfloat16, device=dev) for _ in range(P)]
+    single = torch.empty(B * T * S, C, dtype=torch.bfloat16, device=dev)
+    tiles = osb.HeadTiles(B * S * T, osb.tile_map(0, T), 3, H, D, dev)
+    osb.gemm_head_tiles(x.transpose(1, 2).reshape(B * S * T, C).contiguous(), w, None, tiles, nkinds=3)
+    osb.attn_tiles(tiles, tiles, single, Lk=T, num_seqs=B * S, out_map=osb.tile_map(1, T, S, T))
+    for r in range(P):
+        xr = x[:, :, r * Sl:(r + 1) * Sl].transpose(1, 2).reshape(B * Sl * T, C).contiguous()
+        tr = osb.HeadTiles(B * Sl * T, osb.tile_map(0, T), 3, H, D, dev)
+        osb.gemm_head_tiles(xr, w, None, tr, nkinds=3)
+        osb.attn_tiles(tr, tr, None, Lk=T, num_seqs=B * Sl, out_map=osb.tile_map(1, T, Sl, T),
+                       out_scatter=osb.make_scatter(2, P, r, T, Sl, bufs), out_ld=C)
+    got = torch.cat([b.view(B, Tl, S, C) for b in bufs], 1).reshape(B * T * S, C)
+    assert torch.equal(got, single), "sharded + routed output must be bit-identical to the single-GPU result"

@@ -84,3 +84,26 @@ def test_peer_scatter_routing_equals_all_to_all(P, B, T, S):
         want = full[:, p * Tl:(p + 1) * Tl].reshape(B * Tl * S, C)
         hit = back[p][:, 0] >= 0
         assert hit.any() and torch.equal(back[p][hit], want[hit])
+
+
+def test_transposing_scatter_modes():
+    """Host mirror of osb_scatter modes 3 (local transpose) and 4 (exchange with transposed destination)."""
+    from opensora.acceleration.peer_exchange import scatter_dest
+
+    P, B, T, S = 4, 2, 8, 12
+    Tl, Sl = T // P, S // P
+    full = torch.arange(B * T * S, dtype=torch.float32).view(B, T, S)
+    t3 = torch.full((B * S * T,), -1.0)
+    for row in range(B * T * S):
+        p, d = scatter_dest(3, 1, 0, T, S, row)
+        assert p == 0
+        t3[d] = full.reshape(-1)[row]
+    assert torch.equal(t3.view(B, S, T), full.transpose(1, 2))
+    recv = [torch.full((B * Sl * T,), -1.0) for _ in range(P)]
+    for r in range(P):
+        src = full[:, r * Tl:(r + 1) * Tl].reshape(-1)
+        for row in range(src.numel()):
+            p, d = scatter_dest(4, P, r, Tl, S, row)
+            recv[p][d] = src[row]
+    for p in range(P):
+        assert torch.equal(recv[p].view(B, Sl, T), full[:, :, p * Sl:(p + 1) * Sl].transpose(1, 2))
