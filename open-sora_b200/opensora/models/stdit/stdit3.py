@@ -444,7 +444,6 @@ class STDiT3(nn.Module):
             # (NCCL all-to-all exchange) the GEMM reads them through a strided TMA view instead (mode 1 map).
             ws["tm_out"] = osb.tile_map(1, T, Sl, T)
             ws["tm_t"] = self._tiles(osb, ("temporal", B, T, Sl), B * T * Sl, osb.tile_map(0, T), 3, dev)
-            ws["tm_t_strided"] = (lambda: self._tiles(osb, ("temporal-fm", B, T, Sl), B * T * Sl, ws["tm_out"], 3, dev))
             ws["xm_t"] = torch.empty(R, C, dtype=bf, device=dev) if P == 1 else None
             ws["q_t"] = self._tiles(osb, ("crossq", B, N), R, osb.tile_map(0, N, pack=False), 1, dev)
         else:
@@ -535,7 +534,9 @@ class STDiT3(nn.Module):
                 Sl, xt = S, xm_buf
             ao_t = ao if sp is None else torch.empty_like(ao)
             if tiles:
-                tt = ws["tm_t_strided"]()
+                # (looked up here, not through a closure stored in `ws`: a ws -> lambda -> ws cycle would keep every
+                # forward's workspaces alive until the cyclic GC runs, and the allocator would cudaMalloc new ones each step)
+                tt = self._tiles(osb, ("temporal-fm", B, T, Sl), B * T * Sl, ws["tm_out"], 3, xs.device)
                 osb.gemm_head_tiles(xt, a.qkv.weight, a.qkv.bias, tt, nkinds=3, norm_w=(qn, kn, None), rope=(cos, sin),
                                     rope_kinds=0b011)
                 osb.attn_tiles(tt, tt, ao_t, Lk=T, num_seqs=B * Sl)

@@ -35,6 +35,8 @@ sp_t = osb.HeadTiles(B * N, osb.tile_map(0, S), 3, H, D, dev)
 tm_t = osb.HeadTiles(B * N, osb.tile_map(1, T, S, T), 3, H, D, dev)
 q_t = osb.HeadTiles(B * N, osb.tile_map(0, N, pack=False), 1, H, D, dev)
 kv_t = osb.HeadTiles(B * Ly, osb.tile_map(0, Ly, keys_only=True), 2, H, D, dev)
+tmT_t = osb.HeadTiles(B * N, osb.tile_map(0, T), 3, H, D, dev)
+zsh = torch.zeros(1, C, device=dev)
 osb.gemm_head_tiles(y, wkv, None, kv_t, nkinds=2)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > L2: every timed launch starts cold
 
@@ -62,6 +64,9 @@ cases = [
     ("qkv gemm -> tiles (temporal, no rope, no norm)", lambda: osb.gemm_head_tiles(x, wqkv, bqkv, tm_t, nkinds=3), 2.0 * N * 3 * C * C),
     ("qkv gemm -> tiles (temporal, general)", lambda: osb.gemm_head_tiles(x, wqkv, bqkv, tm_t, nkinds=3, norm_w=(nw, nw, None), rope=(cos, sin), rope_kinds=3, general=True), 2.0 * N * 3 * C * C),
     ("qkv gemm -> tiles (spatial, no norm)", lambda: osb.gemm_head_tiles(x, wqkv, bqkv, sp_t, nkinds=3), 2.0 * N * 3 * C * C),
+    ("qkv gemm -> tiles (temporal, transposed rows)", lambda: osb.gemm_head_tiles(x, wqkv, bqkv, tmT_t, nkinds=3, norm_w=(nw, nw, None), rope=(cos, sin), rope_kinds=3), 2.0 * N * 3 * C * C),
+    ("ln_modulate", lambda: osb.ln_modulate(x, zsh, zsh, group_rows=B * N, out=qc), 4.0 * N * C * 250),
+    ("ln_modulate transposing", lambda: osb.ln_modulate(x, zsh, zsh, group_rows=B * N, scatter=osb.make_scatter(3, 1, 0, T, S, [qc])), 4.0 * N * C * 250),
     ("qkv gemm plain", lambda: osb.gemm(x, wqkv, bqkv, out=qkv), 2.0 * N * 3 * C * C),
     ("q gemm -> tiles (cross)", lambda: osb.gemm_head_tiles(x, wq, None, q_t, nkinds=1), 2.0 * N * C * C),
     ("q gemm plain", lambda: osb.gemm(x, wq, out=qc), 2.0 * N * C * C),
