@@ -213,15 +213,26 @@ def build_model(device):
     per rank; there are no checkpoints offline)."""
     from opensora.registry import MODELS, build_module
 
+    torch.manual_seed(1234)   # module constructors draw from the default generators: identical on every rank
     with torch.device(device):
         m = build_module(dict(type="STDiT3-XL/2"), MODELS).eval()
+    # every parameter and buffer comes from ONE explicitly seeded stream, so all ranks of a multi-GPU run hold the same
+    # model whatever the per-device default generators did (a sequence-parallel run with rank-dependent adaLN tables
+    # cannot match the single-GPU forward)
     g = torch.Generator(device=device).manual_seed(1234)
     with torch.no_grad():
         for n, p in m.named_parameters():
-            if p.dim() >= 2 and "scale_shift_table" not in n:
+            if "scale_shift_table" in n:
+                p.copy_(torch.randn(p.shape, generator=g, device=device) / (p.shape[-1] ** 0.5))
+            elif p.dim() >= 2:
                 p.copy_(torch.randn(p.shape, generator=g, device=device) * (0.7 / (p[0].numel() ** 0.5)))
             elif n.endswith("bias"):
                 p.copy_(0.02 * torch.randn(p.shape, generator=g, device=device))
+            else:   # norm weights
+                p.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=g, device=device))
+        for n, b in m.named_buffers():
+            if b.is_floating_point():
+                b.copy_(torch.randn(b.shape, generator=g, device=device) / (b.shape[-1] ** 0.5))
     return m.to(device=device, dtype=torch.bfloat16)
 
 
@@ -322,7 +333,9 @@ def main():
     if args.graph is None:
         args.graph = mode == "sp"   # 2 048 tokens per rank at N = 8: the step is launch-bound without a graph
     hin = host_inputs(4321 + (rank if mode == "dp" else 0))
-    din = {k: v.to(dev, non_blocking=True) for k, v in hin.items()}
+    # height / width are host scalars (they select the cached positional table; STDiT3.capture documents them as host
+    # values): a device copy would cost one device synchronisation per forward
+    din = {k: (v if k in ("height", "width") else v.to(dev, non_blocking=True)) for k, v in hin.items()}
     sp_check = None
     if mode == "sp":
         # in-run parity of the partition: the sequence-parallel forward against the SAME model's single-GPU forward
@@ -377,7 +390,7 @@ def main():
             if replay is not None:   # host tensors are copied straight into the graph's static inputs
                 o = replay(**hin)
             else:
-                o = model(**{k: v.to(dev, non_blocking=True) for k, v in hin.items()})
+                o = model(**{k: (v if k in ("height", "width") else v.to(dev, non_blocking=True)) for k, v in hin.items()})
             host_out.copy_(o, non_blocking=True)
 
     for _ in range(args.warmup):
@@ -424,7 +437,7 @@ def main():
     if mode == "sp":
         model.enable_sequence_parallel(None)
         hin_dp = host_inputs(4321 + rank)
-        din_dp = {k: v.to(dev, non_blocking=True) for k, v in hin_dp.items()}
+        din_dp = {k: (v if k in ("height", "width") else v.to(dev, non_blocking=True)) for k, v in hin_dp.items()}
 
         def step_dp():
             with torch.no_grad():
@@ -437,7 +450,7 @@ def main():
                     "scaling": "weak", "note": "one independent sample per rank, no data-path collective"}
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            _finish(dist)
         return
     pk = peaks()
     g = fam.get("gemm", [0.0, 1.0, 1])
@@ -485,7 +498,19 @@ def main():
         line["dp_replicas"] = dp_extra
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        _finish(dist)
+
+
+def _finish(dist):
+    """Multi-rank teardown: all work is done and the line is printed; symmetric-memory handles and captured graphs make an
+    orderly interpreter shutdown slow (and it has hung a box) - synchronise, then leave."""
+    torch.cuda.synchronize()
+    try:
+        dist.barrier()
+    except Exception:
+        pass
+    sys.stdout.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":

@@ -686,7 +686,7 @@ extern "C" int osb_attn_tiles(const osb_attn_tiles_args* a, void* stream) {
   p.out = static_cast<__nv_bfloat16*>(a->out);
   p.out_ld = a->out_ld;
   p.scale_log2 = a->softmax_scale * 1.4426950408889634f;
-  { const char* e = getenv("OSB_TA_EXP"); p.exp_flags = e ? atoi(e) : 0; }
+  { static const int exp_flags = [] { const char* e = getenv("OSB_TA_EXP"); return e ? atoi(e) : 0; }(); p.exp_flags = exp_flags; }
   {
     const int64_t out_rows = a->num_seqs * m.L;
     const int rc = make_row_scatter(&p.out_sc, a->out_scatter, out_rows, "osb_attn_tiles");

@@ -56,6 +56,9 @@ class PeerExchange:
                 enable(self.group_name)
             except Exception:
                 pass   # newer torch: implicit
+        import os
+
+        self._debug_sync = os.environ.get("OSB_SP_DEBUG_SYNC", "0") == "1"
         self._bufs: dict = {}
         flags, self._flag_ptrs = self._alloc((64,), torch.int32)
         flags.zero_()
@@ -80,4 +83,8 @@ class PeerExchange:
         return self._osb.make_scatter(mode, self.P, self.rank, I, J, peer_ptrs)
 
     def barrier(self) -> None:
+        if self._debug_sync:   # OSB_SP_DEBUG_SYNC=1: host-side barrier instead of the flag kernel (debugging aid)
+            torch.cuda.synchronize(self.device)
+            dist.barrier(self.group)
+            return
         self._osb.comm_barrier(self.P, self.rank, self.epoch, self._flag_ptrs[self.rank], self._flag_ptrs)

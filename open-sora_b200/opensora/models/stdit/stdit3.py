@@ -429,9 +429,16 @@ class STDiT3(nn.Module):
 
         # ---- workspaces reused by every block ------------------------------------------------------
         R = B * N
-        xm_buf = torch.empty(R, C, dtype=bf, device=dev)
-        ao = torch.empty(R, C, dtype=bf, device=dev)
-        hid = torch.empty(R, int(C * self.config.mlp_ratio), dtype=bf, device=dev)
+
+        def wsbuf(name, *shape):   # block workspaces live with the model (no allocator traffic per step, graph-safe)
+            key = ("ws", name, shape, dev)
+            if key not in self._cache:
+                self._cache[key] = torch.empty(*shape, dtype=bf, device=dev)
+            return self._cache[key]
+
+        xm_buf = wsbuf("xm", R, C)
+        ao = wsbuf("ao", R, C)
+        hid = wsbuf("hid", R, int(C * self.config.mlp_ratio))
         cos, sin = self._rope(T, dev)
         ws = dict(xm=xm_buf, ao=ao, hid=hid, cos=cos, sin=sin, kv=kv_all, kv_lens=kv_lens, tiles=use_tiles,
                   peer=self._peer_exchange(dev) if P > 1 else None)
@@ -444,11 +451,11 @@ class STDiT3(nn.Module):
             # (NCCL all-to-all exchange) the GEMM reads them through a strided TMA view instead (mode 1 map).
             ws["tm_out"] = osb.tile_map(1, T, Sl, T)
             ws["tm_t"] = self._tiles(osb, ("temporal", B, T, Sl), B * T * Sl, osb.tile_map(0, T), 3, dev)
-            ws["xm_t"] = torch.empty(R, C, dtype=bf, device=dev) if P == 1 else None
+            ws["xm_t"] = wsbuf("xm_t", R, C) if P == 1 else None
             ws["q_t"] = self._tiles(osb, ("crossq", B, N), R, osb.tile_map(0, N, pack=False), 1, dev)
         else:
-            ws["qkv"] = torch.empty(R, 3 * C, dtype=bf, device=dev)
-            ws["qc"] = torch.empty(R, C, dtype=bf, device=dev)
+            ws["qkv"] = wsbuf("qkv", R, 3 * C)
+            ws["qc"] = wsbuf("qc", R, C)
 
         bi = 0
         for sb, tb in zip(self.spatial_blocks, self.temporal_blocks):

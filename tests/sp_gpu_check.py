@@ -32,16 +32,19 @@ def main():
         xm = torch.ones(B, T, dtype=torch.bool, device="cuda")
         xm[0, 1] = False
         for x_mask in (None, xm):
-            with torch.no_grad():
-                single = prod(**inp, x_mask=x_mask)
-                prod.enable_sequence_parallel(dist.group.WORLD)
-                sp = prod(**inp, x_mask=x_mask)
-                prod.enable_sequence_parallel(None)
-            r = rel_l2(sp, single)
-            same = torch.equal(sp, single)
-            print(f"[sp{world}] rank {rank} {cfg_name} B{B} {T}x{H}x{W} x_mask={x_mask is not None}: "
-                  f"rel_l2 vs single-GPU = {r:.3e} bit_identical={same}", flush=True)
-            ok &= r < 2e-3
+            for exchange in ("peer", "nccl"):
+                with torch.no_grad():
+                    single = prod(**inp, x_mask=x_mask)
+                    prod.enable_sequence_parallel(dist.group.WORLD, exchange=exchange)
+                    sp = prod(**inp, x_mask=x_mask)
+                    sp2 = prod(**inp, x_mask=x_mask)    # a second step through the same exchange buffers / epochs
+                    kind = prod.sp_exchange_kind
+                    prod.enable_sequence_parallel(None)
+                r = rel_l2(sp, single)
+                same = torch.equal(sp, single) and torch.equal(sp2, single)
+                print(f"[sp{world}] rank {rank} {cfg_name} B{B} {T}x{H}x{W} x_mask={x_mask is not None} exchange={exchange} "
+                      f"({kind[:40]}): rel_l2 vs single-GPU = {r:.3e} bit_identical={same}", flush=True)
+                ok &= r < 2e-3
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
