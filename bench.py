@@ -351,6 +351,7 @@ def main():
         flag = torch.tensor([1.0 if sp_check["rel_l2"] < 2e-3 else 0.0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         sp_check["all_ranks_ok"] = bool(flag.item() == 1.0)
+        sp_check["exchange"] = model.sp_exchange_kind
         del single, spo
 
     def barrier():
@@ -493,7 +494,7 @@ def main():
     }
     if sp_check is not None:
         line["sp_check"] = sp_check
-        line["config"]["exchange"] = getattr(model, "sp_exchange_kind", "nccl all_to_all_single")
+        line["config"]["exchange"] = sp_check.get("exchange")
     if dp_extra is not None:
         line["dp_replicas"] = dp_extra
     print(json.dumps(line), flush=True)
