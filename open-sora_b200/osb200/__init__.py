@@ -404,8 +404,7 @@ def tile_map(mode: int, L: int, S: int = 0, T: int = 0, *, keys_only: bool = Fal
     """Token row -> (tile, row) map of include/osb200.h `osb_tile_map`.  mode 0: sequences are contiguous blocks of L
     rows; mode 1: sequences run along T of a frame-major [B, T, S] token stream (L == T).  Short sequences (L <= 64) are
     packed 128 // L per tile (self-attention: a tile is its own key set; `pack=False` for cross-attention queries,
-    whose key set is per sequence); `keys_only` (text keys of cross-attention) balances the tiles instead:
-    ceil(L / 128) tiles of equal size."""
+    whose key set is per sequence); `keys_only` (text keys of cross-attention) never packs either."""
     m = TileMap()
     m.mode, m.L, m.S, m.T = mode, L, S, T
     if L <= 64 and pack and not keys_only:
@@ -414,7 +413,9 @@ def tile_map(mode: int, L: int, S: int = 0, T: int = 0, *, keys_only: bool = Fal
     else:
         m.G = 1
         n = -(-L // 128)
-        m.tile_rows = 128 if (L > 128 and not keys_only) else -(-(-(-L // n)) // 16) * 16
+        # (keys-only tiles used to be balanced, 300 -> 3 x 112; a 112-row tile ends in the middle of a 32-column softmax
+        # chunk and sent a quarter of the chunks through the per-element masked path: full 128-row tiles + a short last one)
+        m.tile_rows = 128 if L > 128 else -(-(-(-L // n)) // 16) * 16
         m.tps = -(-L // m.tile_rows)
     return m
 

@@ -331,7 +331,9 @@ def tile_map(mode: int, L: int, S: int = 0, T: int = 0, *, keys_only: bool = Fal
     else:
         m.G = 1
         n = -(-L // 128)
-        m.tile_rows = 128 if (L > 128 and not keys_only) else -(-(-(-L // n)) // 16) * 16
+        # (keys-only tiles used to be balanced, 300 -> 3 x 112; a 112-row tile ends in the middle of a 32-column softmax
+        # chunk and sent a quarter of the chunks through the per-element masked path: full 128-row tiles + a short last one)
+        m.tile_rows = 128 if L > 128 else -(-(-(-L // n)) // 16) * 16
         m.tps = -(-L // m.tile_rows)
     return m
 

@@ -166,7 +166,7 @@ def test_tile_map_arithmetic():
 
     assert km(0, 256) == (0, 256, 0, 0, 1, 2, 128)                  # STDiT3 spatial: 2 tiles per sequence
     assert km(1, 64, 256, 64) == (1, 64, 256, 64, 2, 1, 128)        # temporal: 2 sequences per tile
-    assert km(0, 300, keys_only=True) == (0, 300, 0, 0, 1, 3, 112)  # T5 keys: 3 balanced tiles
+    assert km(0, 300, keys_only=True) == (0, 300, 0, 0, 1, 3, 128)  # T5 keys: 128 + 128 + 44
     assert km(0, 16384, pack=False) == (0, 16384, 0, 0, 1, 128, 128)
     assert km(0, 64, pack=False) == (0, 64, 0, 0, 1, 1, 64)         # cross-attention queries are never packed
     assert km(1, 17, 100, 17) == (1, 17, 100, 17, 7, 1, 128)        # 7 x 17 = 119 rows -> 128
