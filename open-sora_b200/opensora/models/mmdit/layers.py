@@ -148,8 +148,18 @@ def _check(x: Tensor):
 
 
 def _rope(pe):
-    """(cos, sin, rotate_half) for the attention kernel: EmbedND -> interleaved pairs, LigerEmbedND -> rotate-half."""
-    return rope_tables(pe)
+    """(cos, sin, rotate_half) for the attention kernel: EmbedND -> interleaved pairs, LigerEmbedND -> rotate-half.  The
+    tables depend only on `pe`, which every block of a forward (and, with a cached `pe`, every step) shares: they are memoised on
+    the tensor itself (57 slicing + contiguous passes per step otherwise)."""
+    host = pe if isinstance(pe, Tensor) else pe[0]
+    hit = getattr(host, "_osb_rope_tables", None)
+    if hit is None or hit[0] != host._version:
+        hit = (host._version, rope_tables(pe))
+        try:
+            host._osb_rope_tables = hit
+        except Exception:   # a tensor subclass that refuses attributes: just recompute
+            pass
+    return hit[1]
 
 
 class _ProcessorBase:
@@ -184,8 +194,14 @@ class _ProcessorBase:
     @staticmethod
     def _modulation(osb, mod: nn.Module, vec: Tensor):
         """layers.py:186-192 on osb200: lin(silu(vec)) -> fp32 [B, C] row views (row stride multiplier*C) the kernels take
-        as shift / scale / gate."""
-        out = osb.gemm(torch.nn.functional.silu(vec).contiguous(), mod.lin.weight, mod.lin.bias).float()
+        as shift / scale / gate.  When the model has already projected `vec` through EVERY block's modulation layer in one
+        grouped GEMM (MMDiTModel.forward_ckpt: SURVEY.md 8f-2), the result rides on `vec` and this block takes its columns."""
+        grouped = getattr(vec, "_osb_grouped_modulation", None)
+        if grouped is not None and id(mod.lin) in grouped[1]:
+            lo, hi = grouped[1][id(mod.lin)]
+            out = grouped[0][:, lo:hi]
+        else:
+            out = osb.gemm(torch.nn.functional.silu(vec).contiguous(), mod.lin.weight, mod.lin.bias).float()
         mult = getattr(mod, "multiplier", None) or (mod.lin.out_features // mod.lin.in_features)
         c = out.chunk(mult, dim=-1)
         return ModulationOut(*c[:3]), (ModulationOut(*c[3:6]) if mult >= 6 else None)

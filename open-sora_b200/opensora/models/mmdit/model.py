@@ -78,10 +78,43 @@ class MMDiTModel(nn.Module):
         self.forward = self.forward_ckpt  # the reference rebinds forward the same way (model.py:143-146)
         self._input_requires_grad = False
         self._cond_w = None
+        self._mod_pack = None
+        self._pe_cache = None
+        self.register_load_state_dict_post_hook(lambda m, k: m._drop_caches())
+
+    def _drop_caches(self):
+        self._cond_w = self._mod_pack = self._pe_cache = None
 
     def _apply(self, fn, *a, **k):
-        self._cond_w = None
+        self._drop_caches()
         return super()._apply(fn, *a, **k)
+
+    # ---- per-step constants ------------------------------------------------------------------
+    def _grouped_modulation(self, vec: Tensor) -> None:
+        """All 2*19 + 38 `Modulation.lin` projections of `vec` as ONE GEMM (the reference launches 76 tiny ones per step,
+        layers.py:179-192).  The fp32 result and the column range of every layer ride on `vec`; the processors pick their
+        slice (a processor installed on a block this model does not own simply does its own projection)."""
+        import osb200
+
+        if self._mod_pack is None:
+            lins = [m.lin for b in self.double_blocks for m in (b.img_mod, b.txt_mod)] + [b.modulation.lin for b in self.single_blocks]
+            cols, off = {}, 0
+            for lin in lins:
+                cols[id(lin)] = (off, off + lin.out_features)
+                off += lin.out_features
+            self._mod_pack = (torch.cat([l.weight for l in lins], 0).contiguous(), torch.cat([l.bias for l in lins], 0).contiguous(), cols)
+        w, b, cols = self._mod_pack
+        out = osb200.gemm(torch.nn.functional.silu(vec).contiguous(), w, b).float()
+        vec._osb_grouped_modulation = (out, cols)
+
+    def _pe(self, txt_ids: Tensor, img_ids: Tensor):
+        """`pe_embedder(cat(txt_ids, img_ids))` is step-invariant (utils/sampling.py:437-447 builds the ids once per sample):
+        cached on the identity and version of the id tensors the caller passes."""
+        key = (id(txt_ids), txt_ids._version, id(img_ids), img_ids._version, tuple(txt_ids.shape), tuple(img_ids.shape), txt_ids.device)
+        if self._pe_cache is None or self._pe_cache[0] != key:
+            # the tensors are kept alive with the entry, so an id() cannot be recycled while it is the key
+            self._pe_cache = (key, self.pe_embedder(torch.cat((txt_ids, img_ids), dim=1)), txt_ids, img_ids)
+        return self._pe_cache[1]
 
     def initialize_weights(self):
         if self.config.cond_embed:
@@ -124,14 +157,14 @@ class MMDiTModel(nn.Module):
             vec = vec + self.guidance_in(timestep_embedding(guidance, 256).to(dt))
         vec = vec + self.vector_in(y_vec)
         txt = self._lin3(txt, self.txt_in)
-        ids = torch.cat((txt_ids, img_ids), dim=1)
-        pe = self.pe_embedder(ids)
+        pe = self._pe(txt_ids, img_ids)
         return img, txt, vec, pe
 
     def forward_ckpt(self, img: Tensor, img_ids: Tensor, txt: Tensor, txt_ids: Tensor, timesteps: Tensor, y_vec: Tensor,
                      cond: Tensor = None, guidance: Tensor | None = None, **kwargs) -> Tensor:
         """model.py:208-233."""
         img, txt, vec, pe = self.prepare_block_inputs(img, img_ids, txt, txt_ids, timesteps, y_vec, cond, guidance)
+        self._grouped_modulation(vec)
         for block in self.double_blocks:
             img, txt = block(img, txt, vec, pe)
         img = torch.cat((txt, img), 1)

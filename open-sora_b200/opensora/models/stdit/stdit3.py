@@ -164,6 +164,7 @@ class STDiT3(nn.Module):
         self._sp_group = None
         self._peer = None
         self._sp_exchange = "nccl"
+        self._sp_config_checked = False
         self.register_load_state_dict_post_hook(lambda m, k: m._cache.clear())
 
     # ---- construction helpers ---------------------------------------------------------------
@@ -205,6 +206,18 @@ class STDiT3(nn.Module):
     def _apply(self, fn, *a, **k):  # .to()/.cuda()/.bfloat16() invalidate the packed-weight cache
         self._cache = {}
         return super()._apply(fn, *a, **k)
+
+    def _configured_sp_group(self):
+        """Upstream's switch: `enable_sequence_parallelism=True` in the config + the group registered with
+        `opensora.acceleration.parallel_states.set_sequence_parallel_group` (parallel_states.py:18-23)."""
+        if self._sp_group is None and self.config.enable_sequence_parallelism and not self._sp_config_checked:
+            from opensora.acceleration.parallel_states import get_sequence_parallel_group
+
+            self._sp_config_checked = True
+            group = get_sequence_parallel_group()
+            if group is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
+                self.enable_sequence_parallel(group)
+        return self._sp_group
 
     def enable_sequence_parallel(self, group, exchange: str | None = None) -> None:
         """Shard tokens over `group`: T-sharded for spatial / cross / MLP, transposed to
@@ -350,7 +363,7 @@ class STDiT3(nn.Module):
         T, H, W = self.get_dynamic_size(x)
         S = H * W
         # sequence parallelism: this rank owns frames [t0, t0+Tl) for every token-local op
-        sp = self._sp_group
+        sp = self._configured_sp_group()
         P = dist.get_world_size(sp) if sp is not None else 1
         if P > 1:
             if T % P or S % P:

@@ -123,3 +123,30 @@ def test_processors_run_on_the_reference_own_blocks(fake_osb, fused):
         assert got.shape == ref.shape and r < max(2.0 * rn, 6e-3), (r, rn)
     names = [c[0] for c in fake_osb.calls]
     assert names.count("attn_short") == (2 if fused else 3) and "ln_modulate" in names
+
+
+def test_per_step_constants_are_hoisted(fake_osb):
+    """ONE grouped GEMM projects `vec` through every block's modulation layer (the reference launches
+    2*depth + depth_single tiny ones), and `pe` is computed once for id tensors that do not change between steps."""
+    m = _rand_model(True)
+    C, nd, ns = CFG["hidden_size"], CFG["depth"], CFG["depth_single_blocks"]
+    txt_ids, img_ids = _ids(1, 8, 1, 4, 4)
+    bf = torch.bfloat16
+    inp = dict(img=torch.randn(1, 16, 64).to(bf), img_ids=img_ids, txt=torch.randn(1, 8, 128).to(bf), txt_ids=txt_ids,
+               timesteps=torch.tensor([0.5]), y_vec=torch.randn(1, 96).to(bf), cond=torch.randn(1, 16, 68).to(bf),
+               guidance=torch.tensor([4.0]))
+    calls = []
+    orig = m.pe_embedder.forward
+    m.pe_embedder.forward = lambda ids: (calls.append(1), orig(ids))[1]
+    with torch.no_grad():
+        fake_osb.reset()
+        a = m(**inp)
+        mod_width = (2 * nd * 6 + ns * 3) * C
+        grouped = [c for c in fake_osb.calls if c[0] == "gemm" and c[1][1] == mod_width]
+        single = [c for c in fake_osb.calls if c[0] == "gemm" and c[1][1] in (6 * C, 3 * C) and c[1][0] == 1]
+        assert len(grouped) == 1 and not single, (len(grouped), len(single))
+        b = m(**dict(inp, timesteps=torch.tensor([0.4])))      # next step: same id tensors
+        assert len(calls) == 1, "pe must be cached across steps"
+        m(**dict(inp, img_ids=img_ids.clone()))                # other id tensors: recomputed
+        assert len(calls) == 2
+    assert a.shape == b.shape == (1, 16, 64)

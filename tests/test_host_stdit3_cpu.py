@@ -93,7 +93,14 @@ def _sp_worker(rank, world, port, ret):
             single = prod(**inp, x_mask=xm)
             prod.enable_sequence_parallel(dist.group.WORLD)
             sharded = prod(**inp, x_mask=xm)
-        ret[rank] = bool(torch.equal(single, sharded))
+            # the reference's own switch: config flag + opensora.acceleration.parallel_states registry
+            from opensora.acceleration.parallel_states import set_sequence_parallel_group
+
+            prod.enable_sequence_parallel(None)
+            prod.config.enable_sequence_parallelism = True
+            set_sequence_parallel_group(dist.group.WORLD)
+            via_config = prod(**inp, x_mask=xm)
+        ret[rank] = bool(torch.equal(single, sharded)) and bool(torch.equal(single, via_config)) and prod._sp_group is not None
     finally:
         dist.destroy_process_group()
 

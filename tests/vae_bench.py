@@ -13,14 +13,6 @@ import torch
 ENC_TF, DEC_TF = 545.8, 1017.9  # algorithmic conv TFLOP at 65x720x1280
 
 
-def conv_flops(model, T, H, W):
-    """Algorithmic conv FLOPs 2*k^3*Cin*Cout*T_o*H_o*W_o of encoder and decoder, from the module tree."""
-    import osb200
-
-    tot = {"enc": 0.0, "dec": 0.0}
-    return tot
-
-
 def run(T=65, H=720, W=1280, iters=2, do_encode=True):
     import osb200
     from opensora.registry import MODELS, build_module
