@@ -70,3 +70,22 @@ def split_forward_gather_backward(input_, process_group, dim, grad_scale=1.0):
 def gather_forward_split_backward(input_, process_group, dim, grad_scale=None):
     """communications.py:187-188 — forward = all-gather and concatenate along `dim`."""
     return _gather(input_, process_group, dim)
+
+
+def gather_forward_split_backward_var_len(input_: torch.Tensor, dim: int, process_group, splits) -> torch.Tensor:
+    """Forward of the reference's var-len gather (`opensora/models/mmdit/distributed.py:671-679`): rank r holds
+    `splits[r]` entries along `dim`; every rank ends up with the concatenation in rank order.  Chunks are padded to the
+    longest one for ONE `all_gather_into_tensor`."""
+    P = _world(process_group)
+    if P == 1:
+        return input_
+    dim %= input_.dim()
+    mx = max(int(v) for v in splits)
+    x = input_.movedim(dim, 0).contiguous()
+    assert x.shape[0] == int(splits[dist.get_rank(process_group)])
+    if x.shape[0] < mx:
+        x = torch.cat([x, x.new_zeros((mx - x.shape[0],) + tuple(x.shape[1:]))], 0)
+    flat = torch.empty((P * mx,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(flat, x, group=process_group)
+    parts = [flat[r * mx:r * mx + int(splits[r])] for r in range(P)]
+    return torch.cat(parts, 0).movedim(0, dim).contiguous()

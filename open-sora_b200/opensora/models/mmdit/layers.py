@@ -162,6 +162,51 @@ def _rope(pe):
     return hit[1]
 
 
+# Sequence parallelism (Ulysses, the reference's `all_to_all` mode: opensora/models/mmdit/distributed.py:473-495): the joint
+# txt|img sequence is split into P equal chunks; around attention q, k, v are exchanged "scatter heads / gather sequence" and
+# the output back.  MMDiTModel sets the group for the duration of a forward; a processor running outside of it sees None.
+_SP = {"group": None}
+
+
+def _sp_group():
+    return _SP["group"]
+
+
+def _sp_attention(osb, qkv: Tensor, out_cols: int, B: int, Lloc: int, H: int, D: int, attn_kw: dict, norm_split_full: int,
+                  dtype, device) -> Tensor:
+    """softmax(q k^T) v over the FULL joint sequence from this rank's [B*Lloc, 3*H*D] q|k|v rows: heads are scattered and
+    the sequence gathered with one all-to-all (q, k, v travel together), attention runs on H/P heads, and the output comes
+    back with the inverse exchange.  Without a group it is the plain local attention."""
+    import torch.distributed as dist
+
+    from opensora.acceleration.communications import all_to_all
+
+    g = _sp_group()
+    P = dist.get_world_size(g) if g is not None else 1
+    C = H * D
+    if P == 1:
+        ao = torch.empty(B * Lloc, out_cols, dtype=dtype, device=device)
+        osb.attn_short(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], ao[:, :C], num_seqs=B, seqs_per_batch=1,
+                       q_strides=(Lloc, 0, 1), k_strides=(Lloc, 0, 1), Lq=Lloc, Lk=Lloc, num_heads=H, head_dim=D,
+                       norm_split=norm_split_full, **attn_kw)
+        return ao
+    if H % P:
+        raise ValueError(f"sequence parallel size {P} must divide the head count {H} (distributed.py:477-479)")
+    Hp, L = H // P, Lloc * P
+    full = all_to_all(qkv.view(B, Lloc, 3, H, D), g, scatter_dim=3, gather_dim=1).reshape(B * L, 3 * Hp * D)
+    Cp = Hp * D
+    ao_full = torch.empty(B * L, Cp, dtype=dtype, device=device)
+    osb.attn_short(full[:, :Cp], full[:, Cp:2 * Cp], full[:, 2 * Cp:], ao_full, num_seqs=B, seqs_per_batch=1,
+                   q_strides=(L, 0, 1), k_strides=(L, 0, 1), Lq=L, Lk=L, num_heads=Hp, head_dim=D,
+                   norm_split=norm_split_full, **attn_kw)
+    back = all_to_all(ao_full.view(B, L, Hp, D), g, scatter_dim=1, gather_dim=2).reshape(B * Lloc, C)
+    if out_cols == C:
+        return back
+    ao = torch.empty(B * Lloc, out_cols, dtype=dtype, device=device)
+    ao[:, :C] = back
+    return ao
+
+
 class _ProcessorBase:
     """What both processors share.  A processor holds NO model weights and touches only attributes the reference's own
     block classes have (`opensora/models/mmdit/layers.py:138-176,256-306,337-388`), so it can be installed with
@@ -208,43 +253,51 @@ class _ProcessorBase:
 
 
 class DoubleStreamBlockProcessor(_ProcessorBase):
-    """osb200 implementation of layers.py:195-253."""
+    """osb200 implementation of layers.py:195-253 (and, under sequence parallelism, of distributed.py:473-495)."""
 
     def __call__(self, attn: nn.Module, img: Tensor, txt: Tensor, vec: Tensor, pe) -> tuple[Tensor, Tensor]:
         osb = _check(img)
         B, Li, C = img.shape
-        Lt = txt.shape[1]
+        Lt = txt.shape[1]            # may be 0 on a sequence-parallel rank whose chunk holds image tokens only
         L, H = Lt + Li, attn.num_heads
         D = C // H
         im1, im2 = self._modulation(osb, attn.img_mod, vec)
         tm1, tm2 = self._modulation(osb, attn.txt_mod, vec)
         img2, txt2 = img.reshape(B * Li, C).contiguous(), txt.reshape(B * Lt, C).contiguous()
-        xi = osb.ln_modulate(img2, im1.shift, im1.scale, group_rows=Li)
-        xt = osb.ln_modulate(txt2, tm1.shift, tm1.scale, group_rows=Lt)
         # q|k|v of both streams land in ONE joint [B*(Lt+Li), 3C] buffer in txt-then-img token order (layers.py:240-242)
         qkv = torch.empty(B * L, 3 * C, dtype=img.dtype, device=img.device)
         wi, bi = self._qkv(attn, attn.img_attn, "img_qkv")
         wt, bt = self._qkv(attn, attn.txt_attn, "txt_qkv")
+        if Li:
+            xi = osb.ln_modulate(img2, im1.shift, im1.scale, group_rows=Li)
+        if Lt:
+            xt = osb.ln_modulate(txt2, tm1.shift, tm1.scale, group_rows=Lt)
         for b in range(B):
-            osb.gemm(xt[b * Lt:(b + 1) * Lt], wt, bt, out=qkv[b * L:b * L + Lt])
-            osb.gemm(xi[b * Li:(b + 1) * Li], wi, bi, out=qkv[b * L + Lt:(b + 1) * L])
+            if Lt:
+                osb.gemm(xt[b * Lt:(b + 1) * Lt], wt, bt, out=qkv[b * L:b * L + Lt])
+            if Li:
+                osb.gemm(xi[b * Li:(b + 1) * Li], wi, bi, out=qkv[b * L + Lt:(b + 1) * L])
         cos, sin, half = _rope(pe)
-        ao = torch.empty(B * L, C, dtype=img.dtype, device=img.device)
-        osb.attn_short(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], ao, num_seqs=B, seqs_per_batch=1, q_strides=(L, 0, 1),
-                       k_strides=(L, 0, 1), Lq=L, Lk=L, num_heads=H, head_dim=D,
-                       q_norm_w=attn.txt_attn.norm.query_norm.scale, k_norm_w=attn.txt_attn.norm.key_norm.scale,
-                       q_norm_w2=attn.img_attn.norm.query_norm.scale, k_norm_w2=attn.img_attn.norm.key_norm.scale,
-                       norm_split=Lt, rope_cos=cos, rope_sin=sin, rope_half=half)
+        kw = dict(q_norm_w=attn.txt_attn.norm.query_norm.scale, k_norm_w=attn.txt_attn.norm.key_norm.scale,
+                  q_norm_w2=attn.img_attn.norm.query_norm.scale, k_norm_w2=attn.img_attn.norm.key_norm.scale,
+                  rope_cos=cos, rope_sin=sin, rope_half=half)
+        # tokens at joint position >= the FULL text length take the image stream's QK-norm weights
+        split_full = getattr(vec, "_osb_txt_len", Lt)
+        ao = _sp_attention(osb, qkv, C, B, L, H, D, kw, split_full, img.dtype, img.device)
         img_o, txt_o = torch.empty_like(img2), torch.empty_like(txt2)
         for b in range(B):  # x + gate * proj(attn)   (layers.py:247, 251)
-            osb.gemm(ao[b * L + Lt:(b + 1) * L], attn.img_attn.proj.weight, attn.img_attn.proj.bias,
-                     epilogue=osb.EPI_BIAS_GATE_RES, residual=img2[b * Li:(b + 1) * Li], gate=im1.gate[b:b + 1],
-                     out=img_o[b * Li:(b + 1) * Li])
-            osb.gemm(ao[b * L:b * L + Lt], attn.txt_attn.proj.weight, attn.txt_attn.proj.bias,
-                     epilogue=osb.EPI_BIAS_GATE_RES, residual=txt2[b * Lt:(b + 1) * Lt], gate=tm1.gate[b:b + 1],
-                     out=txt_o[b * Lt:(b + 1) * Lt])
+            if Li:
+                osb.gemm(ao[b * L + Lt:(b + 1) * L], attn.img_attn.proj.weight, attn.img_attn.proj.bias,
+                         epilogue=osb.EPI_BIAS_GATE_RES, residual=img2[b * Li:(b + 1) * Li], gate=im1.gate[b:b + 1],
+                         out=img_o[b * Li:(b + 1) * Li])
+            if Lt:
+                osb.gemm(ao[b * L:b * L + Lt], attn.txt_attn.proj.weight, attn.txt_attn.proj.bias,
+                         epilogue=osb.EPI_BIAS_GATE_RES, residual=txt2[b * Lt:(b + 1) * Lt], gate=tm1.gate[b:b + 1],
+                         out=txt_o[b * Lt:(b + 1) * Lt])
         # x + gate * MLP((1 + scale) * LN(x) + shift)   (layers.py:248, 252)
         for x_o, mod, mlp, n in ((img_o, im2, attn.img_mlp, Li), (txt_o, tm2, attn.txt_mlp, Lt)):
+            if n == 0:
+                continue
             xm = osb.ln_modulate(x_o, mod.shift, mod.scale, group_rows=n)
             hid = osb.gemm(xm, mlp[0].weight, mlp[0].bias, epilogue=osb.EPI_BIAS_GELU_TANH)
             osb.gemm(hid, mlp[2].weight, mlp[2].bias, epilogue=osb.EPI_BIAS_GATE_RES, residual=x_o, gate=mod.gate,
@@ -306,13 +359,12 @@ class SingleStreamBlockProcessor(_ProcessorBase):
         xm = osb.ln_modulate(x2, mod.shift, mod.scale, group_rows=L)
         wq, bq, wm, bm = self._split_weights(attn)
         qkv = osb.gemm(xm, wq, bq)                                               # [B*L, 3C]
-        cat = torch.empty(B * L, C + M4, dtype=x.dtype, device=x.device)         # [attn | gelu(mlp)] side by side
-        osb.gemm(xm, wm, bm, epilogue=osb.EPI_BIAS_GELU_TANH, out=cat[:, C:])
         cos, sin, half = _rope(pe)
-        osb.attn_short(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], cat[:, :C], num_seqs=B, seqs_per_batch=1,
-                       q_strides=(L, 0, 1), k_strides=(L, 0, 1), Lq=L, Lk=L, num_heads=H, head_dim=D,
-                       q_norm_w=attn.norm.query_norm.scale, k_norm_w=attn.norm.key_norm.scale, rope_cos=cos, rope_sin=sin,
-                       rope_half=half)
+        kw = dict(q_norm_w=attn.norm.query_norm.scale, k_norm_w=attn.norm.key_norm.scale, rope_cos=cos, rope_sin=sin,
+                  rope_half=half)
+        # [attn | gelu(mlp)] side by side: the attention output and the GELU GEMM write one [rows, C + 4C] buffer
+        cat = _sp_attention(osb, qkv, C + M4, B, L, H, D, kw, 0, x.dtype, x.device)
+        osb.gemm(xm, wm, bm, epilogue=osb.EPI_BIAS_GELU_TANH, out=cat[:, C:])
         out = osb.gemm(cat, attn.linear2.weight, attn.linear2.bias, epilogue=osb.EPI_BIAS_GATE_RES, residual=x2,
                        gate=mod.gate, group_rows=L)
         return out.view(B, L, C)

@@ -80,6 +80,7 @@ class MMDiTModel(nn.Module):
         self._cond_w = None
         self._mod_pack = None
         self._pe_cache = None
+        self._sp_group = None
         self.register_load_state_dict_post_hook(lambda m, k: m._drop_caches())
 
     def _drop_caches(self):
@@ -160,18 +161,62 @@ class MMDiTModel(nn.Module):
         pe = self._pe(txt_ids, img_ids)
         return img, txt, vec, pe
 
+    def enable_sequence_parallel(self, group) -> None:
+        """Ulysses sequence parallelism over `group` (the reference's `all_to_all` mode, opensora/models/mmdit/
+        distributed.py:473-495,598-634,671-679): the joint txt|img sequence is split into P equal chunks (a rank holds the tail
+        of the text and/or a slice of the image tokens), every token-local op runs on the chunk, attention exchanges
+        "scatter heads / gather sequence" on q|k|v (ONE all-to-all for the three) and back on the output, and the image
+        tokens are all-gathered (var-len) after the final layer.  `None` switches it off."""
+        self._sp_group = group
+
+    def _sp_splits(self, Lt: int, Li: int):
+        """(P, rank, [txt tokens per rank], [img tokens per rank]) of the equal split of the joint sequence, or None when
+        sequence parallelism is off / not applicable (distributed.py:604-617: a rank without image tokens disables it)."""
+        import torch.distributed as dist
+
+        g = getattr(self, "_sp_group", None)
+        if g is None or not dist.is_initialized() or dist.get_world_size(g) == 1:
+            return None
+        P, r = dist.get_world_size(g), dist.get_rank(g)
+        if (Lt + Li) % P:
+            raise ValueError(f"Expected {Lt + Li} % {P} == 0 (distributed.py:600-604)")
+        ch = (Lt + Li) // P
+        txt_s = [max(0, min((k + 1) * ch, Lt) - min(k * ch, Lt)) for k in range(P)]
+        img_s = [ch - t for t in txt_s]
+        if 0 in img_s:
+            return None
+        return P, r, txt_s, img_s
+
     def forward_ckpt(self, img: Tensor, img_ids: Tensor, txt: Tensor, txt_ids: Tensor, timesteps: Tensor, y_vec: Tensor,
                      cond: Tensor = None, guidance: Tensor | None = None, **kwargs) -> Tensor:
-        """model.py:208-233."""
+        """model.py:208-233; with a sequence-parallel group: distributed.py:598-681 (forward part)."""
+        from . import layers as L_
+
         img, txt, vec, pe = self.prepare_block_inputs(img, img_ids, txt, txt_ids, timesteps, y_vec, cond, guidance)
         self._grouped_modulation(vec)
-        for block in self.double_blocks:
-            img, txt = block(img, txt, vec, pe)
-        img = torch.cat((txt, img), 1)
-        for block in self.single_blocks:
-            img = block(img, vec, pe)
-        img = img[:, txt.shape[1]:, ...]
-        return self.final_layer(img, vec)
+        Lt, Li = txt.shape[1], img.shape[1]
+        sp = self._sp_splits(Lt, Li)
+        vec._osb_txt_len = Lt   # joint positions >= Lt take the image stream's QK-norm weights on every rank
+        if sp is not None:
+            P, r, txt_s, img_s = sp
+            t0, i0 = sum(txt_s[:r]), sum(img_s[:r])
+            txt, img = txt[:, t0:t0 + txt_s[r]].contiguous(), img[:, i0:i0 + img_s[r]].contiguous()
+        prev = L_._SP["group"]
+        L_._SP["group"] = self._sp_group if sp is not None else None
+        try:
+            for block in self.double_blocks:
+                img, txt = block(img, txt, vec, pe)
+            x = torch.cat((txt, img), 1)
+            for block in self.single_blocks:
+                x = block(x, vec, pe)
+        finally:
+            L_._SP["group"] = prev
+        out = self.final_layer(x[:, txt.shape[1]:, ...].contiguous(), vec)
+        if sp is not None:
+            from opensora.acceleration.communications import gather_forward_split_backward_var_len
+
+            out = gather_forward_split_backward_var_len(out, 1, self._sp_group, sp[3])
+        return out
 
     forward_selective_ckpt = forward_ckpt
 
