@@ -88,30 +88,46 @@ class DecoderCausal3D(nn.Module):
 
 
 class DiagonalGaussianDistribution:
-    """vae.py:280-340 (NCDHW parameters; trivial elementwise work, kept in torch)."""
+    """vae.py:280-340.  The posterior over the latent: `parameters` holds mean | logvar along the channel axis (axis 1 for
+    image / video tensors, the last axis for token tensors [B, L, C]).  Elementwise work on a latent-sized tensor, kept in
+    torch."""
 
     def __init__(self, parameters: torch.Tensor, deterministic: bool = False):
+        if parameters.ndim == 3:
+            axis = 2
+        elif parameters.ndim in (4, 5):
+            axis = 1
+        else:
+            raise NotImplementedError(f"posterior parameters with {parameters.ndim} dimensions")
         self.parameters = parameters
-        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
-        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
         self.deterministic = deterministic
-        self.std = torch.exp(0.5 * self.logvar)
-        self.var = torch.exp(self.logvar)
-        if self.deterministic:
-            self.var = self.std = torch.zeros_like(self.mean)
+        self.mean, logvar = parameters.chunk(2, dim=axis)
+        self.logvar = logvar.clamp(-30.0, 20.0)
+        if deterministic:
+            self.std = self.var = torch.zeros_like(self.mean)
+        else:
+            self.std, self.var = (0.5 * self.logvar).exp(), self.logvar.exp()
 
     def sample(self, generator=None) -> torch.Tensor:
-        noise = torch.randn(self.mean.shape, generator=generator, device=self.parameters.device, dtype=self.parameters.dtype)
-        return self.mean + self.std * noise
+        eps = torch.randn(self.mean.shape, generator=generator, device=self.parameters.device, dtype=self.parameters.dtype)
+        return self.mean + self.std * eps
 
     def kl(self, other=None) -> torch.Tensor:
         if self.deterministic:
             return torch.Tensor([0.0])
-        red = list(range(1, self.mean.ndim))
-        if other is None:
-            return 0.5 * torch.sum(torch.pow(self.mean, 2) + self.var - 1.0 - self.logvar, dim=red)
-        return 0.5 * torch.sum(torch.pow(self.mean - other.mean, 2) / other.var + self.var / other.var - 1.0
-                               - self.logvar + other.logvar, dim=red)
+        axes = list(range(1, self.mean.ndim))
+        if other is None:   # against N(0, I)
+            terms = self.mean.pow(2) + self.var - 1.0 - self.logvar
+        else:
+            terms = (self.mean - other.mean).pow(2) / other.var + self.var / other.var - 1.0 - self.logvar + other.logvar
+        return 0.5 * terms.sum(dim=axes)
+
+    def nll(self, sample: torch.Tensor, dims=(1, 2, 3)) -> torch.Tensor:
+        if self.deterministic:
+            return torch.Tensor([0.0])
+        import math
+
+        return 0.5 * (math.log(2.0 * math.pi) + self.logvar + (sample - self.mean).pow(2) / self.var).sum(dim=list(dims))
 
     def mode(self) -> torch.Tensor:
         return self.mean

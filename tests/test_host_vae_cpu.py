@@ -92,3 +92,34 @@ def test_causal_conv_is_causal_and_latent_size_api(fake_osb):
         z = m.encode(v, sample_posterior=False)
         rec, _, z2 = m(v, sample_posterior=False)
     assert list(z.shape) == [1, 4] + m.get_latent_size([9, 32, 32]) and rec.shape == v.shape and torch.equal(z, z2)
+
+
+def test_posterior_distribution_matches_the_reference_class():
+    """`DiagonalGaussianDistribution` (sample with a seeded generator, kl with and without a second distribution, nll, mode,
+    the deterministic switch, token-shaped parameters) against the reference's own class executed by path."""
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        pytest.skip("reference checkout not present (GPU box)")
+    _, Rvae = ref_loader.load_hunyuan_vae()
+    from opensora.models.hunyuan_vae.vae import DiagonalGaussianDistribution as Ours
+
+    g = torch.Generator().manual_seed(5)
+    for shape in ((2, 8, 3, 4, 5), (2, 8, 6, 7), (2, 9, 8)):
+        par = torch.randn(*shape, generator=g) * 3.0
+        par2 = torch.randn(*shape, generator=g)
+        a, b = Ours(par), Rvae.DiagonalGaussianDistribution(par)
+        a2, b2 = Ours(par2), Rvae.DiagonalGaussianDistribution(par2)
+        assert torch.equal(a.mode(), b.mode()) and torch.equal(a.std, b.std) and torch.equal(a.logvar, b.logvar)
+        sa = a.sample(torch.Generator().manual_seed(11))
+        sb = b.sample(torch.Generator().manual_seed(11))
+        assert torch.equal(sa, sb) and sa.shape == a.mean.shape
+        torch.testing.assert_close(a.kl(), b.kl(), rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(a.kl(a2), b.kl(b2), rtol=1e-6, atol=1e-6)
+        if par.ndim >= 4:
+            dims = list(range(1, par.ndim))
+            torch.testing.assert_close(a.nll(sa, dims), b.nll(sb, dims), rtol=1e-6, atol=1e-5)
+        d = Ours(par, deterministic=True)
+        assert torch.equal(d.sample(), d.mean) and float(d.kl()) == 0.0 and float(d.nll(sa)) == 0.0
+    with pytest.raises(NotImplementedError):
+        Ours(torch.zeros(4, 4))
