@@ -69,7 +69,9 @@ def test_mmdit_model_vs_pinned_oracle(fused, liger, thw):
     rn = rel_l2(noise, ref)
     print(f"[parity] reference-in-bf16 noise floor rel_l2={rn:.3e}")
     assert out.shape == ref.shape
-    assert r < 2e-2 and r < max(1.5 * rn, 5e-3)
+    # measured 4.9e-3 in all four layouts (profiles/r02_parity_report.txt) against a reference-in-bf16 floor of 3.5e-2:
+    # the bar is 2x the measured value, not the noise floor
+    assert r < 1.0e-2 and r < rn
 
 
 def test_processor_hook_is_the_plugin_point():

@@ -5,7 +5,8 @@ Tolerance (north_star: 'within 1e-3 rel of the reference', made meaningful for b
 hard part 2): the product rounds the residual stream and every GEMM output to bf16 exactly where the
 reference's own bf16 path does, so its error vs the fp32 oracle must not exceed the error of the
 oracle itself run in bf16 (the reference-precision noise floor, measured in the same test) by more
-than 1.5x, and must stay below an absolute 2e-2 rel-L2."""
+than 1.1x (measured ratios 0.77 - 0.97, profiles/r02_parity_report.txt), and must stay below an absolute
+1.5e-2 (depth 2) / 3e-2 (depth 28) rel-L2."""
 import pytest
 import torch
 
@@ -40,7 +41,8 @@ def test_xs_parity(B, T, H, W):
     rn = rel_l2(noise, ref)
     print(f"[parity] oracle-in-bf16 noise floor rel_l2={rn:.3e}")
     assert out.shape == ref.shape
-    assert r < 2e-2 and r < max(1.5 * rn, 4e-3)
+    # measured 7.4e-3 / 7.6e-3 against the oracle's own bf16 error 9.6e-3 / 9.4e-3 (profiles/r02_parity_report.txt)
+    assert r < 1.5e-2 and r < 1.1 * rn
 
 
 def test_xs_x_mask_and_ragged_text():
@@ -52,7 +54,7 @@ def test_xs_x_mask_and_ragged_text():
     out, ref, noise = _run("xs", 2, 6, 8, 8, x_mask=xm, lens=[300, 17])
     r, _ = report("STDiT3-XS/2 x_mask", out, ref)
     rn = rel_l2(noise, ref)
-    assert r < 2e-2 and r < max(1.5 * rn, 4e-3)
+    assert r < 1.5e-2 and r < 1.1 * rn
 
 
 def test_xl_parity_reduced_latent():
@@ -63,7 +65,7 @@ def test_xl_parity_reduced_latent():
     r, _ = report("STDiT3-XL/2 16x16x16", out, ref)
     rn = rel_l2(noise, ref)
     print(f"[parity] oracle-in-bf16 noise floor rel_l2={rn:.3e}")
-    assert r < 3e-2 and r < max(1.5 * rn, 6e-3)
+    assert r < 3e-2 and r < 1.1 * rn   # measured 2.15e-2 against a floor of 2.22e-2
 
 
 def _block_trace(prod, oracle, inp):
@@ -118,7 +120,7 @@ def test_xl_parity_at_the_benchmark_shape():
     assert per_block[0] < 5e-3, per_block[0]
     for k in range(1, len(per_block)):
         assert per_block[k] < 3.0 * per_block[k - 1] + 2e-3, (k, per_block[k - 1], per_block[k])
-    assert r < 3e-2 and r < max(1.5 * rn, 6e-3), (r, rn)
+    assert r < 3e-2 and r < 1.1 * rn, (r, rn)   # measured 2.16e-2 against a floor of 2.23e-2
 
 
 def test_register_path_matches_tile_path(monkeypatch):

@@ -159,10 +159,10 @@ def test_encoder_decoder_against_reference_goldens(osb):
     xin = m._to_ndhwc(G["enc_x"].cuda().to(torch.bfloat16), cpad=8)
     z = m._to_ncdhw(m.encoder(xin))
     r, _ = report("encoder vs reference golden", z, G["enc_y"].cuda())
-    assert z.shape == G["enc_y"].shape and r < max(1.5 * fe, 1e-2)
+    assert z.shape == G["enc_y"].shape and r < 1.15 * fe   # measured 1.07e-2 against the reference-in-bf16 floor 1.27e-2
     y = m._to_ncdhw(m.decoder(m._to_ndhwc(G["enc_y"][:, :4].cuda().to(torch.bfloat16))))
     r, _ = report("decoder vs reference golden", y, G["dec_y"].cuda())
-    assert y.shape == G["dec_y"].shape and r < max(1.5 * fd, 1e-2)
+    assert y.shape == G["dec_y"].shape and r < fd          # measured 2.11e-2 against 3.04e-2
 
 
 def test_autoencoder_roundtrip_api(osb):
@@ -232,4 +232,5 @@ def test_tiled_modes_against_reference_goldens(osb, tag, sp, tp):
     ry, _ = report(f"tiled decode [{tag}]", y, GT[f"y_{tag}"].cuda())
     print(f"[parity] reference-in-bf16 noise floor: encode {zf:.3e} decode {yf:.3e}")
     assert z.shape == GT[f"z_{tag}"].shape and y.shape == GT[f"y_{tag}"].shape
-    assert rz < max(1.5 * zf, 1e-2) and ry < max(1.5 * yf, 1e-2)
+    # measured: encode 0.71 - 0.96 of the reference-in-bf16 floor, decode 0.66 - 0.78 (profiles/r02_parity_report.txt)
+    assert rz < 1.1 * zf and ry < yf
