@@ -175,3 +175,15 @@ def test_tile_map_arithmetic():
     assert osb200._lib.osb_head_tiles_per_head(ctypes.byref(m), 5 * 200) == 10
     m = osb200.tile_map(1, 16, 12, 16)
     assert osb200._lib.osb_head_tiles_per_head(ctypes.byref(m), 2 * 16 * 12) == 3   # 24 sequences, 8 per tile
+
+
+def test_stand_in_tile_map_equals_the_binding():
+    """tests/fake_osb200.py restates `tile_map`; the host tests are only meaningful if both agree on every shape."""
+    import osb200
+    from tests import fake_osb200
+
+    for mode in (0, 1):
+        for L in (1, 7, 16, 17, 32, 48, 64, 65, 100, 128, 129, 200, 256, 300, 1200, 16384):
+            for kw in ({}, {"keys_only": True}, {"pack": False}):
+                S, T = (12, L) if mode == 1 else (0, 0)
+                assert fake_osb200.tile_map(mode, L, S, T, **kw).key() == osb200.tile_map(mode, L, S, T, **kw).key(), (mode, L, kw)
