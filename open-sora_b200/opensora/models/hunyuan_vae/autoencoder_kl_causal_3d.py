@@ -98,6 +98,19 @@ class AutoencoderKLCausal3D(nn.Module):
     def disable_slicing(self):
         self.use_slicing = False
 
+    def enable_temporal_parallel(self, process_group=None):
+        """Shard the decoder's up path by frames over `process_group` (one process per GPU; None switches it off).  Every
+        rank passes the SAME latent to `decode` and gets the whole video back: conv_in + mid block run replicated, the up
+        blocks - over nine tenths of the decode's flops, more of its bytes - on this rank's run of frames with a two-frame causal halo from the
+        left neighbour and group-wide GroupNorm statistics (unet_causal_3d_blocks._TemporalShard), one gather at the end.
+        No reference counterpart (single-GPU VAE, tiled when short of memory); composes with spatial tiling, and temporal
+        tiles too short to shard are decoded replicated."""
+        import torch.distributed as dist
+
+        if process_group is not None and dist.get_world_size(process_group) == 1:
+            process_group = None
+        self.decoder.shard_group = process_group
+
     # ---- helpers -------------------------------------------------------------------------------------
     def _check(self):
         import osb200

@@ -20,6 +20,79 @@ def _osb():
     return osb200
 
 
+class _TemporalShard:
+    """Frame-sharded decode (SURVEY.md 8e "VAE T-shard with halo").  While `group` is set, every rank of it holds a contiguous
+    run of frames of the same video (rank order = frame order) and each 3x3x3 `CausalConv3d`
+      * normalises with GroupNorm statistics over ALL ranks' frames (per-rank mean / variance combined with their element
+        counts - the parallel-variance identity, so no second pass over the activations), and
+      * takes the two causal context frames it needs from its left neighbour (one point-to-point message per convolution)
+        instead of the replicate padding, which only rank 0 - the owner of the first frame - applies.
+    The reference has no counterpart (its VAE runs on one GPU, tiled when memory is short: autoencoder_kl_causal_3d.py:
+    454-560); results equal the un-sharded decode up to the rounding of the combined statistics."""
+
+    group = None
+
+
+class temporal_shard:
+    """`with temporal_shard(group): ...` - scope in which CausalConv3d treats its input as this rank's frame run."""
+
+    def __init__(self, group):
+        self.group = group
+
+    def __enter__(self):
+        self.prev, _TemporalShard.group = _TemporalShard.group, self.group
+        return self
+
+    def __exit__(self, *exc):
+        _TemporalShard.group = self.prev
+        return False
+
+
+def frame_partition(frames: int, parts: int) -> list[int]:
+    """Contiguous split of `frames` over `parts` ranks, the remainder on the lowest ranks (rank 0 owns the first frame, whose
+    upsampling rule differs)."""
+    base, rem = divmod(frames, parts)
+    return [base + (1 if r < rem else 0) for r in range(parts)]
+
+
+def _combine_group_stats(stats, count: int, eps: float, group):
+    """(mean, rstd) fp32 [nb, G, 2] of this rank's `count` elements per group -> the statistics of the union over the group's
+    ranks: mean = sum n_r m_r / N,  var = sum n_r (v_r + (m_r - mean)^2) / N  (no cancellation, so fp32 is enough)."""
+    import torch.distributed as dist
+
+    P = dist.get_world_size(group)
+    mean, rstd = stats[..., 0], stats[..., 1]
+    var = (1.0 / (rstd * rstd) - eps).clamp_min(0.0)
+    mine = torch.stack((mean, var, torch.full_like(mean, float(count))), dim=-1).contiguous()
+    flat = torch.empty((P * mine.shape[0],) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
+    dist.all_gather_into_tensor(flat, mine, group=group)   # rank-major concatenation along dim 0
+    every = flat.view((P,) + tuple(mine.shape))
+    m, v, n = every[..., 0].double(), every[..., 1].double(), every[..., 2].double()
+    total = n.sum(0)
+    gmean = (n * m).sum(0) / total
+    gvar = (n * (v + (m - gmean) ** 2)).sum(0) / total
+    return torch.stack((gmean, torch.rsqrt(gvar + eps)), dim=-1).float().contiguous()
+
+
+def _left_halo(x, frames: int, group):
+    """Send my last `frames` frames to the right neighbour, return the left neighbour's (None on rank 0)."""
+    import torch.distributed as dist
+
+    P, r = dist.get_world_size(group), dist.get_rank(group)
+    if x.shape[1] < frames:
+        raise ValueError(f"temporal shard: {x.shape[1]} local frame(s), the causal halo needs {frames}")
+    ops, halo = [], None
+    if r + 1 < P:
+        tail = x[:, -frames:].contiguous()
+        ops.append(dist.P2POp(dist.isend, tail, dist.get_global_rank(group, r + 1), group))
+    if r > 0:
+        halo = torch.empty((x.shape[0], frames) + tuple(x.shape[2:]), dtype=x.dtype, device=x.device)
+        ops.append(dist.P2POp(dist.irecv, halo, dist.get_global_rank(group, r - 1), group))
+    for w in dist.batch_isend_irecv(ops) if ops else ():
+        w.wait()
+    return halo
+
+
 class CausalConv3d(nn.Module):
     """Parameter container + launcher.  `forward(x, norm=..., silu=..., up=..., residual=...)`: the optional
     GroupNorm(+SiLU) and nearest upsample that PRECEDE this convolution in the reference are folded into the
@@ -73,12 +146,26 @@ class CausalConv3d(nn.Module):
             return y.view(nb, T, H, W, wp.shape[0])
         stats = gamma = beta = None
         groups = 1
+        shard = _TemporalShard.group
         if norm is not None:
             groups = norm.num_groups
             stats = osb.group_stats(x, groups, norm.eps)
             gamma, beta = norm.weight, norm.bias
+            if shard is not None:
+                stats = _combine_group_stats(stats, T * H * W * (C // groups), norm.eps, shard)
+        pad_t = self.kernel_size - 1
+        if shard is not None:
+            # Causal context across the shard boundary.  The two (upsampled) frames in front of my first one are: the left
+            # neighbour's last two frames (no temporal upsample), or two copies of its last frame (x2 upsample - also when
+            # that frame is the video's first, whose single copy the replicate padding doubles).  With the x2 upsample the
+            # halo frame lands on the "first frame" rule (one copy) and one replicate-padded frame supplies the second.
+            assert self.kernel_size == 3 and self.stride == (1, 1, 1), "temporal shard: 3x3x3 stride-1 convolutions only"
+            halo = _left_halo(x, 2 if up[0] == 1 else 1, shard)
+            if halo is not None:
+                x = torch.cat((halo, x), dim=1)
+                pad_t = 0 if up[0] == 1 else 1
         xp = osb.vae_prep(x, stats=stats, gamma=gamma, beta=beta, groups=groups, silu=silu, up=up,
-                          pad=(self.kernel_size - 1, self.kernel_size // 2, self.kernel_size // 2), cp=cp)
+                          pad=(pad_t, self.kernel_size // 2, self.kernel_size // 2), cp=cp)
         tp, hp, wpd = xp.shape[1:4]
         st, sh, sw = self.stride
         k = self.kernel_size

@@ -7,9 +7,13 @@ from __future__ import annotations
 import math
 
 import torch
+import torch.distributed as dist
 import torch.nn as nn
 
-from .unet_causal_3d_blocks import CausalConv3d, DownEncoderBlockCausal3D, UNetMidBlockCausal3D, UpDecoderBlockCausal3D
+from opensora.acceleration.communications import gather_forward_split_backward_var_len
+
+from .unet_causal_3d_blocks import (CausalConv3d, DownEncoderBlockCausal3D, UNetMidBlockCausal3D, UpDecoderBlockCausal3D,
+                                    frame_partition, temporal_shard)
 
 
 def _plan(n_blocks, time_compression_ratio, spatial_compression_ratio):
@@ -79,12 +83,34 @@ class DecoderCausal3D(nn.Module):
         self.conv_act = nn.SiLU()
         self.conv_out = CausalConv3d(block_out_channels[0], out_channels, kernel_size=3)
 
+        self.time_upsample = time_compression_ratio
+        self.shard_group = None   # set by AutoencoderKLCausal3D.enable_temporal_parallel
+
     def forward(self, sample):  # NDHWC bf16 latent
         x = self.conv_in(sample)
         x = self.mid_block(x)
-        for blk in self.up_blocks:
-            x = blk(x)
-        return self.conv_out(x, norm=self.conv_norm_out, silu=True)
+        group = self.shard_group
+        # fewer than 2 latent frames per rank (the causal halo is 2 frames deep): every rank decodes the whole (tile of the)
+        # latent - same result on every rank, no exchange
+        if group is None or x.shape[1] < 2 * dist.get_world_size(group):
+            for blk in self.up_blocks:
+                x = blk(x)
+            return self.conv_out(x, norm=self.conv_norm_out, silu=True)
+        # Frame-sharded decode: conv_in + the mid block (latent resolution, frame-causal attention over all frames: under a tenth
+        # of the decode's flops) run replicated, then each rank keeps its run of latent frames through the up blocks - where the
+        # activations grow 4 x 8 x 8 fold - and the pixel frames are gathered once at the end.
+        P, r = dist.get_world_size(group), dist.get_rank(group)
+        counts = frame_partition(x.shape[1], P)
+        first = sum(counts[:r])
+        x = x[:, first:first + counts[r]].contiguous()
+        with temporal_shard(group):
+            for blk in self.up_blocks:
+                x = blk(x)
+            x = self.conv_out(x, norm=self.conv_norm_out, silu=True)
+        f = self.time_upsample
+        out_frames = [f * c - (f - 1 if q == 0 else 0) for q, c in enumerate(counts)]   # the first frame is not repeated
+        assert x.shape[1] == out_frames[r], (x.shape, out_frames, r)
+        return gather_forward_split_backward_var_len(x, 1, group, out_frames)
 
 
 class DiagonalGaussianDistribution:

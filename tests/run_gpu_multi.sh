@@ -7,6 +7,10 @@ nvidia-smi topo -m > gpurun_out/topo_$N.txt 2>&1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 echo "=== sp parity check ($N GPUs)"
 timeout 600 $TR --master-port 29511 tests/sp_gpu_check.py 2>&1 | grep -E "sp$N|SP_CHECK|Error|error|Warning" | tee gpurun_out/r02_sp_check_$N.log | tail -n 24
+if [ -n "${VAE_TP:-}" ]; then
+  echo "=== frame-sharded VAE decode check ($N GPUs)"
+  timeout 600 $TR --master-port 29513 tests/vae_tp_gpu_check.py 2>&1 | grep -E "vae-tp|VAE_TP|Error|error" | tee gpurun_out/vae_tp_check_$N.log | tail -n 20
+fi
 for mode in ${MODES:-sp}; do
   echo "=== bench --parallel $mode ($N GPUs)"
   timeout 900 $TR --master-port 29512 bench.py --gpus $N --steps 10 --warmup 3 --parallel $mode ${BENCH_FLAGS:-} > gpurun_out/bench_${mode}_$N.json 2> gpurun_out/bench_${mode}_$N.err

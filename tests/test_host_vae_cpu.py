@@ -123,3 +123,107 @@ def test_posterior_distribution_matches_the_reference_class():
         assert torch.equal(d.sample(), d.mean) and float(d.kl()) == 0.0 and float(d.nll(sa)) == 0.0
     with pytest.raises(NotImplementedError):
         Ours(torch.zeros(4, 4))
+
+
+def _tp_worker(rank, world, port, ret):
+    import sys
+
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests import fake_osb200
+
+        sys.modules["osb200"] = fake_osb200
+        import opensora.models.hunyuan_vae.unet_causal_3d_blocks as U
+        from opensora.acceleration.communications import gather_forward_split_backward_var_len
+
+        torch.manual_seed(11)   # the same model on every rank (quant / post_quant convolutions are not in the golden file)
+        G = _golden("vae_blocks.npz")
+        m = _model(G, sample_size=32, sample_tsize=8).to(torch.bfloat16)
+        real_stats, real_combine = fake_osb200.group_stats, U._combine_group_stats
+
+        def whole_video_stats(x, groups, eps=1e-6):
+            """Statistics of the gathered frames through the SAME routine the un-sharded decode uses: isolates the halo /
+            padding / up-sampling logic (bit-level comparison) from the rounding of the combined statistics."""
+            g = U._TemporalShard.group
+            if g is None:
+                return real_stats(x, groups, eps)
+            lens = [torch.zeros(1, dtype=torch.long) for _ in range(world)]
+            dist.all_gather(lens, torch.tensor([x.shape[1]]), group=g)
+            return real_stats(gather_forward_split_backward_var_len(x, 1, g, [int(v) for v in lens]), groups, eps)
+
+        torch.manual_seed(3)
+        out = {}
+        # 7 latent frames: 4 + 3 (world 2) / 3 + 2 + 2 (world 3) -> every rank >= the 2-frame halo; 3 frames: too few to
+        # shard, decoded replicated
+        for name, z in (("z7", torch.randn(2, 4, 7, 8, 8)), ("z3", torch.randn(1, 4, 3, 8, 8))):
+            with torch.no_grad():
+                m.enable_temporal_parallel(None)
+                fake_osb200.reset()
+                whole = m.decode(z)
+                whole_frames = sum(c[1][0][1] for c in fake_osb200.calls if c[0] == "vae_prep")
+                m.enable_temporal_parallel(dist.group.WORLD)
+                fake_osb200.reset()
+                sharded = m.decode(z)
+                shard_frames = sum(c[1][0][1] for c in fake_osb200.calls if c[0] == "vae_prep")
+                fake_osb200.group_stats, U._combine_group_stats = whole_video_stats, (lambda s, *a: s)
+                try:
+                    exact = m.decode(z)
+                finally:
+                    fake_osb200.group_stats, U._combine_group_stats = real_stats, real_combine
+                m.enable_spatial_tiling(True)      # 8x8 latent > the 4x4 tile: every spatial tile is frame-sharded too
+                tiled_sharded = m.decode(z)
+                m.enable_temporal_parallel(None)
+                tiled = m.decode(z)
+                m.enable_spatial_tiling(False)
+            out[name] = dict(shapes=(tuple(whole.shape), tuple(sharded.shape), tuple(exact.shape)), rel=rel_l2(sharded, whole),
+                             rel_exact_stats=rel_l2(exact, whole), bit_identical=bool(torch.equal(exact, whole)),
+                             rel_tiled=rel_l2(tiled_sharded, tiled), frames=(whole_frames, shard_frames))
+        ret[rank] = out
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("world", [2, 3])
+def test_frame_sharded_decode_matches_the_whole_decode(world):
+    """SURVEY.md 8e "VAE T-shard with halo": the decoder's up path sharded by frames over `world` gloo ranks (two-frame causal
+    halo from the left neighbour, GroupNorm statistics combined over the ranks, first-frame up-sampling rule on rank 0 only)
+    against the same model decoding the whole latent on one rank.
+      * with the statistics taken from the gathered frames by the un-sharded routine, every convolution sees the same bf16
+        inputs as in the whole decode: the outputs must agree to fp32 summation-order noise (the halo logic is exact);
+      * with the real combination (per-rank mean / variance + counts) the statistics differ in the last fp32 bits, which
+        flips bf16 roundings through ~25 normalised layers: same size as the model's own bf16 noise, bounded here."""
+    import torch.multiprocessing as mp
+
+    port = 29500 + (os.getpid() + 11 * world) % 2000
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_tp_worker, args=(world, port, ret), nprocs=world, join=True)
+    for r in range(world):
+        print(r, dict(ret[r]))
+        for name, o in ret[r].items():
+            assert o["shapes"][0] == o["shapes"][1] == o["shapes"][2], (r, name, o)
+            assert o["rel_exact_stats"] < 1e-3, (r, name, o)
+            assert o["rel"] < 1.5e-2 and o["rel_tiled"] < 1.5e-2, (r, name, o)
+        whole_frames, shard_frames = ret[r]["z7"]["frames"]
+        assert shard_frames < 0.8 * whole_frames, (r, whole_frames, shard_frames)   # really worked on a share of the frames
+        assert ret[r]["z3"]["frames"][0] == ret[r]["z3"]["frames"][1]                 # too short to shard: replicated
+
+
+def test_frame_partition_and_stat_combination():
+    from opensora.models.hunyuan_vae.unet_causal_3d_blocks import frame_partition
+
+    assert frame_partition(17, 8) == [3, 2, 2, 2, 2, 2, 2, 2] and frame_partition(8, 2) == [4, 4] and sum(frame_partition(33, 4)) == 33
+    # the identity _combine_group_stats uses, against a direct computation
+    torch.manual_seed(0)
+    parts = [torch.randn(n) * s + o for n, s, o in ((50, 1.0, 3.0), (20, 0.2, -1.0), (130, 2.0, 0.5))]
+    n = torch.tensor([float(p.numel()) for p in parts]).double()
+    m = torch.stack([p.double().mean() for p in parts])
+    v = torch.stack([p.double().var(unbiased=False) for p in parts])
+    gm = (n * m).sum() / n.sum()
+    gv = (n * (v + (m - gm) ** 2)).sum() / n.sum()
+    whole = torch.cat(parts).double()
+    assert abs(gm - whole.mean()) < 1e-12 and abs(gv - whole.var(unbiased=False)) < 1e-12
