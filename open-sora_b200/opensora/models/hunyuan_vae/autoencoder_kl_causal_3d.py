@@ -301,12 +301,8 @@ def CausalVAE3D_HUNYUAN(from_pretrained: str = None, device_map: str | torch.dev
     config = AutoEncoder3DConfig(from_pretrained=from_pretrained, **{k: v for k, v in kwargs.items() if k in fields})
     model = AutoencoderKLCausal3D(config)
     if from_pretrained:
-        if from_pretrained.endswith(".safetensors"):
-            from safetensors.torch import load_file
+        from opensora.utils.ckpt import load_checkpoint
 
-            sd = load_file(from_pretrained)
-        else:
-            sd = torch.load(from_pretrained, map_location="cpu")
-        model.load_state_dict(sd, strict=True)
+        model = load_checkpoint(model, from_pretrained, device_map="cpu", strict=True)
     return model.to(device=device_map, dtype=torch_dtype) if torch.cuda.is_available() or str(device_map) == "cpu" \
         else model.to(dtype=torch_dtype)

@@ -224,15 +224,12 @@ class MMDiTModel(nn.Module):
 @MODELS.register_module("flux")
 def Flux(cache_dir: str = None, from_pretrained: str = None, device_map: str | torch.device = "cuda",
          torch_dtype: torch.dtype = torch.bfloat16, strict_load: bool = False, **kwargs) -> MMDiTModel:
-    """model.py:271-303 (checkpoint loading: local safetensors / torch files only — no hub access offline)."""
+    """model.py:271-303.  Weights go through `opensora.utils.ckpt.load_checkpoint` like upstream (safetensors / torch file /
+    sharded directory; local or hub-cache paths only - no network here)."""
     config = MMDiTConfig(from_pretrained=from_pretrained, cache_dir=cache_dir, **kwargs)
     model = MMDiTModel(config)
     if from_pretrained:
-        if from_pretrained.endswith(".safetensors"):
-            from safetensors.torch import load_file
+        from opensora.utils.ckpt import load_checkpoint
 
-            sd = load_file(from_pretrained)
-        else:
-            sd = torch.load(from_pretrained, map_location="cpu")
-        model.load_state_dict(sd, strict=strict_load)
+        model = load_checkpoint(model, from_pretrained, cache_dir=cache_dir, device_map="cpu", strict=strict_load)
     return model.to(device=device_map, dtype=torch_dtype)
