@@ -215,9 +215,12 @@ def load_hunyuan_vae(with_autoencoder: bool = False):
 
 def load_sampling():
     """The reference's `opensora/utils/sampling.py` executed by path.  Its top-level imports that are absent here
-    (mmengine, peft, datasets, text encoder, registry, inference helpers) are only used by the prompt / model-loading
-    half of the file; they are replaced by empty stand-ins.  The numeric functions used for goldens
-    (`time_shift`, `get_schedule`, `pack`, `unpack`, `get_oscillation_gs`, `I2VDenoiser.denoise`) are untouched."""
+    (mmengine, peft, text encoder, registry, dataset I/O, prompt refinement) are only used by the model-loading / file
+    half of the file; they are replaced by empty stand-ins.  Everything the goldens exercise is the reference's own code:
+    `time_shift`, `get_schedule`, `pack`, `unpack`, `get_oscillation_gs`, the denoisers, `sanitize_sampling_option` (with
+    the real `datasets/aspect.py`), `prepare`, `prepare_ids`, `prepare_api` (with the real `utils/inference.py`:
+    `prepare_inference_condition`, `collect_references_batch`).  The two helper modules are returned as attributes
+    `ref_aspect` / `ref_inference`."""
     import enum
 
     names = ("opensora", "opensora.utils", "opensora.datasets", "opensora.models", "opensora.models.mmdit",
@@ -236,13 +239,20 @@ def load_sampling():
 
         mod("mmengine.config", Config=type("Config", (), {}))
         sys.modules["peft"].PeftModel = type("PeftModel", (), {})
-        mod("opensora.datasets.aspect", get_image_size=lambda *a, **k: (0, 0))
+        # `datasets/aspect.py` (math + os only) and `utils/inference.py` are executed for real: the option sanitiser and the
+        # conditioning format come from them.  What inference.py imports for file I/O and prompt rewriting is stubbed.
+        aspect = _load("opensora.datasets.aspect", os.path.join(REF, "opensora", "datasets", "aspect.py"))
+        sys.modules["opensora.datasets"].save_sample = None
+        mod("opensora.datasets.utils", read_from_path=None, rescale_image_by_path=None)
+        mod("opensora.utils.logger", log_message=print)
+        mod("opensora.utils.prompt_refine", refine_prompts=None)
+        inference = _load("opensora.utils.inference", os.path.join(REF, "opensora", "utils", "inference.py"))
         mod("opensora.models.mmdit.model", MMDiTModel=type("MMDiTModel", (), {}))
         mod("opensora.models.text.conditioner", HFEmbedder=type("HFEmbedder", (), {}))
         mod("opensora.registry", MODELS=None, build_module=None)
-        mod("opensora.utils.inference", SamplingMethod=enum.Enum("SamplingMethod", {"I2V": "i2v", "DISTILLED": "distill"}),
-            collect_references_batch=None, prepare_inference_condition=None)
-        return _load("opensora.utils.sampling", os.path.join(REF, "opensora", "utils", "sampling.py"))
+        sampling = _load("opensora.utils.sampling", os.path.join(REF, "opensora", "utils", "sampling.py"))
+        sampling.ref_aspect, sampling.ref_inference = aspect, inference
+        return sampling
     finally:
         for k in [k for k in sys.modules if any(k == n or k.startswith(n + ".") for n in ("opensora", "mmengine", "peft"))]:
             del sys.modules[k]

@@ -44,6 +44,78 @@ def main():
     path = os.path.join(HERE, "sampling.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+    pipeline(S)
+
+
+def pipeline(S):
+    """tests/golden/sampling_pipeline.npz: the request-side half of the reference file, executed - option sanitising (with
+    the reference's own datasets/aspect.py), guidance prompts, `prepare` / `prepare_ids`, the conditioning format
+    (utils/inference.py), DistilledDenoiser and `prepare_api` end to end on the toy models of tests/sampling_toys.py."""
+    import json
+
+    from tests import sampling_toys as T
+
+    out, meta = {}, {}
+    A, I = S.ref_aspect, S.ref_inference
+    meta["aspect_inference"] = {res: {k: list(v) for k, v in A.get_aspect_ratios_dict(A.get_num_pexels_from_name(res), False).items()}
+                                for res in ("256px", "768px", "360p", "720p", "1080px")}
+    meta["aspect_training"] = {res: {k: list(v) for k, v in A.get_aspect_ratios_dict(A.get_num_pexels_from_name(res), True).items()}
+                               for res in ("256px", "768px")}
+    san = {}
+    for name, kw in (("res", dict(resolution="768px", aspect_ratio="9:16", method="i2v")), ("hw", dict(height=250, width=443)),
+                     ("hw16", dict(height=256, width=448, method="distill")), ("res360", dict(resolution="360p", aspect_ratio="2.39:1"))):
+        o = S.sanitize_sampling_option(S.SamplingOption(**kw))
+        san[name] = [o.height, o.width, o.method.value]
+    meta["sanitize"] = san
+    t2i = I.modify_option_to_t2i(S.SamplingOption(resolution="256px", aspect_ratio="16:9", num_frames=33, guidance=7.5), distilled=True,
+                                 img_resolution="768px")
+    meta["t2i"] = [t2i.height, t2i.width, t2i.num_frames, t2i.guidance, t2i.method.value, t2i.resized_resolution]
+    meta["guidance_i2v"] = S.I2VDenoiser().prepare_guidance(["a", "b"], {}, "cpu", torch.float32, neg=None, guidance_img=3.0)[0]
+    meta["guidance_i2v_neg"] = S.I2VDenoiser().prepare_guidance(["a"], {}, "cpu", torch.float32, neg=["n"], guidance_img=3.0)[0]
+
+    g = torch.Generator().manual_seed(21)
+    z = torch.randn(1, 4, 3, 8, 12, generator=g)
+    for tag, d in (("prepare", S.prepare(T.toy_t5, T.toy_clip, z, prompt=["a cat", "neg", "neg"])),
+                   ("prepare_ids", S.prepare_ids(z.repeat(2, 1, 1, 1, 1), torch.randn(1, 5, 8, generator=g), torch.randn(1, 8, generator=g)))):
+        for k, v in d.items():
+            out[f"{tag}.{k}"] = v.numpy()
+    out["prepare_z"] = z.numpy()
+    g = torch.Generator().manual_seed(21)
+    torch.randn(1, 4, 3, 8, 12, generator=g)
+    out["ids_t5"], out["ids_clip"] = torch.randn(1, 5, 8, generator=g).numpy(), torch.randn(1, 8, generator=g).numpy()
+
+    # conditioning format, every kind, causal and not
+    zc = torch.zeros(2, 4, 20, 2, 3)
+    refs = [[torch.randn(4, 20, 2, 3, generator=g), torch.randn(4, 20, 2, 3, generator=g)], None]
+    out["cond_refs"] = torch.stack(refs[0]).numpy()
+    for kind in ("t2v", "i2v_head", "i2v_tail", "i2v_loop", "v2v_head", "v2v_tail", "v2v_head_easy", "v2v_tail_easy"):
+        for causal in (True, False):
+            m, mz = I.prepare_inference_condition(zc, kind, ref_list=refs, causal=causal)
+            out[f"cond.{kind}.{int(causal)}.masks"], out[f"cond.{kind}.{int(causal)}.ref"] = m.numpy(), mz.numpy()
+
+    model = T.ToyDenoiser()
+    x0 = torch.randn(2, 24, 16, generator=g)
+    out["distill_x0"] = x0.numpy()
+    out["distill_out"] = S.DistilledDenoiser().denoise(
+        model, img=x0.clone(), timesteps=S.get_schedule(5, 24, 1), guidance=3.5, img_ids=torch.zeros(2, 24, 3), txt=torch.ones(2, 6, 8),
+        txt_ids=torch.zeros(2, 6, 3), y_vec=torch.ones(2, 8)).detach().numpy()
+
+    media = T.reference_media()
+    I.read_from_path = lambda path, image_size, transform_name=None: media[path]
+    for name, opt_kw, call_kw in T.SCENARIOS:
+        ae = T.ToyAE(causal=opt_kw.get("is_causal_vae", False))
+        api = S.prepare_api(model, ae, T.toy_t5, T.toy_clip, {})
+        opt = S.sanitize_sampling_option(S.SamplingOption(**opt_kw))
+        model.seen.clear()
+        x = api(opt, **{k: (list(v) if isinstance(v, list) else v) for k, v in call_kw.items()})
+        out[f"api.{name}"] = x.numpy().astype(np.float16)
+        meta[f"api.{name}.shape"] = list(x.shape)
+        meta[f"api.{name}.model_kwargs"] = model.seen[0]
+        meta[f"api.{name}.calls"] = len(model.seen)
+    out["meta"] = np.array(json.dumps(meta))
+    path = os.path.join(HERE, "sampling_pipeline.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
 if __name__ == "__main__":
