@@ -99,8 +99,9 @@ class AutoencoderKLCausal3D(nn.Module):
         self.use_slicing = False
 
     def enable_temporal_parallel(self, process_group=None):
-        """Shard the decoder's up path by frames over `process_group` (one process per GPU; None switches it off).  Every
-        rank passes the SAME latent to `decode` and gets the whole video back: conv_in + mid block run replicated, the up
+        """Shard the VAE by frames over `process_group` (one process per GPU; None switches it off).  Every rank passes the
+        SAME tensor to `encode` / `decode` and gets the whole result back.  Encoder: conv_in + down blocks on this rank's
+        frames, mid block + conv_out replicated on the gathered latent.  Decoder: conv_in + mid block run replicated, the up
         blocks - over nine tenths of the decode's flops, more of its bytes - on this rank's run of frames with a two-frame causal halo from the
         left neighbour and group-wide GroupNorm statistics (unet_causal_3d_blocks._TemporalShard), one gather at the end.
         No reference counterpart (single-GPU VAE, tiled when short of memory); composes with spatial tiling, and temporal
@@ -110,6 +111,7 @@ class AutoencoderKLCausal3D(nn.Module):
         if process_group is not None and dist.get_world_size(process_group) == 1:
             process_group = None
         self.decoder.shard_group = process_group
+        self.encoder.shard_group = process_group
 
     # ---- helpers -------------------------------------------------------------------------------------
     def _check(self):

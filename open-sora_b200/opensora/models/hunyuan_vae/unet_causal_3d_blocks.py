@@ -28,23 +28,29 @@ class _TemporalShard:
       * takes the two causal context frames it needs from its left neighbour (one point-to-point message per convolution)
         instead of the replicate padding, which only rank 0 - the owner of the first frame - applies.
     The reference has no counterpart (its VAE runs on one GPU, tiled when memory is short: autoencoder_kl_causal_3d.py:
-    454-560); results equal the un-sharded decode up to the rounding of the combined statistics."""
+    454-560); results equal the un-sharded decode up to the rounding of the combined statistics.
+
+    `start` is the global index of this rank's first frame at the current layer.  Only the encoder needs it: a
+    temporally strided convolution reads windows that begin at even (padded) positions, so how many context frames a rank
+    needs from its left neighbour - 2 or 1 - depends on the parity of its first frame; the convolution updates it."""
 
     group = None
+    start = None
 
 
 class temporal_shard:
     """`with temporal_shard(group): ...` - scope in which CausalConv3d treats its input as this rank's frame run."""
 
-    def __init__(self, group):
-        self.group = group
+    def __init__(self, group, start: int | None = None):
+        self.group, self.start = group, start
 
     def __enter__(self):
-        self.prev, _TemporalShard.group = _TemporalShard.group, self.group
+        self.prev = (_TemporalShard.group, _TemporalShard.start)
+        _TemporalShard.group, _TemporalShard.start = self.group, self.start
         return self
 
     def __exit__(self, *exc):
-        _TemporalShard.group = self.prev
+        _TemporalShard.group, _TemporalShard.start = self.prev
         return False
 
 
@@ -74,16 +80,18 @@ def _combine_group_stats(stats, count: int, eps: float, group):
     return torch.stack((gmean, torch.rsqrt(gvar + eps)), dim=-1).float().contiguous()
 
 
-def _left_halo(x, frames: int, group):
-    """Send my last `frames` frames to the right neighbour, return the left neighbour's (None on rank 0)."""
+def _left_halo(x, frames: int, group, send_frames: int | None = None):
+    """Send my last `send_frames` (default `frames`) frames to the right neighbour, return the left neighbour's last
+    `frames` (None on rank 0)."""
     import torch.distributed as dist
 
     P, r = dist.get_world_size(group), dist.get_rank(group)
-    if x.shape[1] < frames:
-        raise ValueError(f"temporal shard: {x.shape[1]} local frame(s), the causal halo needs {frames}")
+    send_frames = frames if send_frames is None else send_frames
+    if x.shape[1] < max(frames, send_frames):
+        raise ValueError(f"temporal shard: {x.shape[1]} local frame(s), the causal halo needs {max(frames, send_frames)}")
     ops, halo = [], None
     if r + 1 < P:
-        tail = x[:, -frames:].contiguous()
+        tail = x[:, -send_frames:].contiguous()
         ops.append(dist.P2POp(dist.isend, tail, dist.get_global_rank(group, r + 1), group))
     if r > 0:
         halo = torch.empty((x.shape[0], frames) + tuple(x.shape[2:]), dtype=x.dtype, device=x.device)
@@ -155,12 +163,23 @@ class CausalConv3d(nn.Module):
                 stats = _combine_group_stats(stats, T * H * W * (C // groups), norm.eps, shard)
         pad_t = self.kernel_size - 1
         if shard is not None:
-            # Causal context across the shard boundary.  The two (upsampled) frames in front of my first one are: the left
-            # neighbour's last two frames (no temporal upsample), or two copies of its last frame (x2 upsample - also when
-            # that frame is the video's first, whose single copy the replicate padding doubles).  With the x2 upsample the
-            # halo frame lands on the "first frame" rule (one copy) and one replicate-padded frame supplies the second.
-            assert self.kernel_size == 3 and self.stride == (1, 1, 1), "temporal shard: 3x3x3 stride-1 convolutions only"
-            halo = _left_halo(x, 2 if up[0] == 1 else 1, shard)
+            # Causal context across the shard boundary.
+            #  * stride 1, no temporal upsample: the two frames in front of my first one = the left neighbour's last two.
+            #  * x2 temporal upsample (decoder): both are copies of its last frame (also when that frame is the video's first,
+            #    whose single copy the replicate padding doubles): the halo frame lands on `osb_vae_prep`'s first-frame rule
+            #    (one copy) and ONE replicate-padded frame supplies the second.
+            #  * temporal stride 2 (encoder): output j reads frames 2j-2 .. 2j; my first output is j0 = ceil(start / 2), so I
+            #    need start - (2 j0 - 2) = 2 (even start) or 1 (odd start) frames of context, and my right neighbour - whose
+            #    first frame is start + T - needs the same rule applied to its own parity.
+            assert self.kernel_size == 3 and self.stride[0] in (1, 2), "temporal shard: 3x3x3 convolutions, temporal stride 1 or 2"
+            if self.stride[0] == 2:
+                assert up[0] == 1 and _TemporalShard.start is not None, "temporal shard: strided convolution needs the frame offset"
+                start = _TemporalShard.start
+                need, give = 2 - start % 2, 2 - (start + T) % 2
+                halo = _left_halo(x, need, shard, send_frames=give)
+                _TemporalShard.start = (start + 1) // 2
+            else:
+                halo = _left_halo(x, 2 if up[0] == 1 else 1, shard)
             if halo is not None:
                 x = torch.cat((halo, x), dim=1)
                 pad_t = 0 if up[0] == 1 else 1

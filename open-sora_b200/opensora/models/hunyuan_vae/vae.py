@@ -52,10 +52,35 @@ class EncoderCausal3D(nn.Module):
         self.conv_act = nn.SiLU()
         self.conv_out = CausalConv3d(block_out_channels[-1], 2 * out_channels if double_z else out_channels, kernel_size=3)
 
+        self.time_downsample = time_compression_ratio
+        self.shard_group = None   # set by AutoencoderKLCausal3D.enable_temporal_parallel
+
     def forward(self, sample):  # NDHWC bf16 (channels padded to a multiple of 8)
-        x = self.conv_in(sample)
-        for blk in self.down_blocks:
-            x = blk(x)
+        group = self.shard_group
+        f = self.time_downsample
+        latent_frames = (sample.shape[1] - 1) // f + 1
+        if group is None or (sample.shape[1] - 1) % f or latent_frames < 2 * dist.get_world_size(group):
+            x = self.conv_in(sample)
+            for blk in self.down_blocks:
+                x = blk(x)
+            x = self.mid_block(x)
+            return self.conv_out(x, norm=self.conv_norm_out, silu=True)
+        # Frame-sharded encode (the mirror image of DecoderCausal3D's): rank r takes the pixel frames of its run of LATENT
+        # frames (rank 0: f c_0 - (f - 1), the others f c_r), so every temporally strided stage ends on a shard boundary;
+        # conv_in and the down blocks - all of the encode's high-resolution work - run on the local frames with the causal
+        # halo and group-wide GroupNorm statistics; the latent-resolution mid block (frame-causal attention over all frames)
+        # and conv_out run replicated on the gathered latent.
+        P, r = dist.get_world_size(group), dist.get_rank(group)
+        counts = frame_partition(latent_frames, P)
+        pixel = [f * c - (f - 1 if q == 0 else 0) for q, c in enumerate(counts)]
+        first = sum(pixel[:r])
+        x = sample[:, first:first + pixel[r]].contiguous()
+        with temporal_shard(group, start=first):
+            x = self.conv_in(x)
+            for blk in self.down_blocks:
+                x = blk(x)
+        assert x.shape[1] == counts[r], (x.shape, counts, r)
+        x = gather_forward_split_backward_var_len(x, 1, group, counts)
         x = self.mid_block(x)
         return self.conv_out(x, norm=self.conv_norm_out, silu=True)
 

@@ -111,6 +111,12 @@ def ln_modulate(x, shift, scale, *, group_rows: int, mod_index=None, eps: float 
     return out
 
 
+# Accumulation dtype of the GEMM / convolution stand-ins.  fp32 by default; a test that compares two decompositions of the
+# SAME computation (e.g. a frame-sharded convolution against the whole one) switches to fp64, where the summation order of
+# the CPU kernels can no longer flip a bf16 rounding, so the comparison can be bit-exact.
+ACC_DTYPE = torch.float32
+
+
 def gemm(a, w, bias=None, *, epilogue: int = EPI_BIAS, residual=None, gate=None, group_rows: int = 0, mod_index=None,
          out=None, cta_group: int = 0, block_n: int = 0):
     for t, n in ((a, "a"), (w, "w"), (bias, "bias"), (residual, "residual"), (out, "out")):
@@ -121,9 +127,9 @@ def gemm(a, w, bias=None, *, epilogue: int = EPI_BIAS, residual=None, gate=None,
     N = w.shape[0]
     if K % 8 or N % 8:
         raise OsbError(f"osb_gemm_bf16 failed (-1): osb_gemm_bf16: K and N must be multiples of 8 (K {K} N {N})")
-    acc = a.float() @ w.float().t()
+    acc = a.to(ACC_DTYPE) @ w.to(ACC_DTYPE).t()
     if bias is not None:
-        acc = acc + bias.float()
+        acc = acc + bias.to(ACC_DTYPE)
     if epilogue == EPI_BIAS_GELU_TANH:
         acc = F.gelu(acc, approximate="tanh")
     elif epilogue == EPI_BIAS_GATE_RES:
@@ -131,7 +137,7 @@ def gemm(a, w, bias=None, *, epilogue: int = EPI_BIAS, residual=None, gate=None,
             g = _groups(M, group_rows if group_rows > 0 else M, mod_index, a.device)
             acc = acc * gate[g]
         if residual is not None:
-            acc = acc + residual.float()
+            acc = acc + residual.to(ACC_DTYPE)
     y = acc.to(torch.bfloat16)
     _count("gemm", (M, N, K, epilogue))
     if out is None:
@@ -283,12 +289,12 @@ def conv3d(x_pad, w_packed, bias, *, out_thw, stride=(1, 1, 1), taps=(3, 3, 3), 
     st, sh, sw = stride
     if (t_out - 1) * st + kt > tp or (h_out - 1) * sh + kh > hp or (w_out - 1) * sw + kw > wp:
         raise OsbError("osb_conv3d_ndhwc: padded input too small for the output")
-    y = F.conv3d(x_pad.float().permute(0, 4, 1, 2, 3), w.permute(0, 4, 1, 2, 3), None, stride=stride)
+    y = F.conv3d(x_pad.to(ACC_DTYPE).permute(0, 4, 1, 2, 3), w.to(ACC_DTYPE).permute(0, 4, 1, 2, 3), None, stride=stride)
     y = y[:, :, :t_out, :h_out, :w_out].permute(0, 2, 3, 4, 1)
     if bias is not None:
-        y = y + bias.float()
+        y = y + bias.to(ACC_DTYPE)
     if residual is not None:
-        y = y + residual.float()
+        y = y + residual.to(ACC_DTYPE)
     _count("conv3d", (tuple(x_pad.shape), cout, stride, narrow))
     return y.to(torch.bfloat16).contiguous()
 
