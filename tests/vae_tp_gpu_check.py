@@ -50,10 +50,17 @@ def main():
 
         with torch.no_grad():
             whole, t_whole = timed(lambda: m.decode(z))
+            video = whole.clamp(-1, 1)
+            lat, t_enc = timed(lambda: m.encode(video, sample_posterior=False))
             m.enable_temporal_parallel(dist.group.WORLD)
             sharded, t_shard = timed(lambda: m.decode(z))
+            lat_sh, t_enc_sh = timed(lambda: m.encode(video, sample_posterior=False))
             m.enable_temporal_parallel(None)
         r = rel_l2(sharded, whole)
+        re = rel_l2(lat_sh, lat)
+        print(f"[vae-tp{world}] rank {rank} {name} encode {tuple(video.shape[2:])} -> {tuple(lat.shape[2:])}: rel_l2 vs whole encode = "
+              f"{re:.3e}  whole {t_enc:.1f} ms  sharded {t_enc_sh:.1f} ms (x{t_enc / t_enc_sh:.2f})", flush=True)
+        ok &= lat_sh.shape == lat.shape and re < 2e-2
         frames = whole.shape[2]
         print(f"[vae-tp{world}] rank {rank} {name} latent {T}x{H}x{W} -> {frames} frames: rel_l2 vs whole decode = {r:.3e}  "
               f"whole {t_whole:.1f} ms ({frames / t_whole * 1e3:.1f} fps)  sharded {t_shard:.1f} ms "
