@@ -11,6 +11,10 @@ if [ -n "${VAE_TP:-}" ]; then
   echo "=== frame-sharded VAE decode check ($N GPUs)"
   timeout 600 $TR --master-port 29513 tests/vae_tp_gpu_check.py 2>&1 | grep -E "vae-tp|VAE_TP|Error|error" | tee gpurun_out/vae_tp_check_$N.log | tail -n 20
 fi
+if [ -n "${MMDIT_SP:-}" ]; then
+  echo "=== MMDiT Ulysses sequence-parallel check ($N GPUs)"
+  timeout 600 $TR --master-port 29514 tests/mmdit_sp_gpu_check.py 2>&1 | grep -E "mmdit-sp|MMDIT_SP|Error|error" | tee gpurun_out/mmdit_sp_check_$N.log | tail -n 20
+fi
 for mode in ${MODES:-sp}; do
   echo "=== bench --parallel $mode ($N GPUs)"
   timeout 900 $TR --master-port 29512 bench.py --gpus $N --steps 10 --warmup 3 --parallel $mode ${BENCH_FLAGS:-} > gpurun_out/bench_${mode}_$N.json 2> gpurun_out/bench_${mode}_$N.err
