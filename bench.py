@@ -364,6 +364,91 @@ def _vae_cpu_baseline():
         return {"error": repr(e)[:200]}
 
 
+# ---- MMDiT leg (SURVEY.md 8d Cfg5 at the 256px shape): its own process, so nothing it does can reach the headline -------------
+MMDIT_256PX = dict(in_channels=64, vec_in_dim=768, context_in_dim=4096, hidden_size=3072, mlp_ratio=4.0, num_heads=24, depth=19,
+                   depth_single_blocks=38, axes_dim=[16, 56, 56], theta=10_000, qkv_bias=True, guidance_embed=False, cond_embed=True,
+                   fused_qkv=False, use_liger_rope=True)   # configs/diffusion/inference/256px.py:36-55
+
+
+def mmdit_leg_main():
+    """`bench.py --leg mmdit`: one denoiser forward of the in-tree MMDiT at the reference's 256px inference shape (B = 3 CFG
+    branches, 33 x 12 x 21 = 8 316 image tokens + 512 text tokens, C = 3072, 24 x 128 heads, 19 + 38 blocks, the shipped
+    `fused_qkv=False` / Liger-RoPE layout), random-init bf16 weights created on the device, inputs resident.  Prints one JSON
+    object.  First written after the round-2 GPU budget was spent: it has never run before the driver runs it."""
+    import osb200
+    from opensora.models.mmdit.model import MMDiTConfig, MMDiTModel
+
+    torch.cuda.set_device(0)
+    osb200.init(0)
+    cfg = MMDIT_256PX
+    B, T, H, W, Lt = 3, 33, 12, 21, 512
+    Li = T * H * W
+    L, C = Li + Lt, cfg["hidden_size"]
+    tflop = B * (cfg["depth"] + cfg["depth_single_blocks"]) * (24.0 * C * C * L + 4.0 * L * L * C) / 1e12   # SURVEY.md 8d
+    torch.manual_seed(0)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        with torch.device("cuda"):
+            model = MMDiTModel(MMDiTConfig(from_pretrained=None, cache_dir=None, **cfg)).eval()
+    finally:
+        torch.set_default_dtype(prev)
+    with torch.no_grad():
+        torch.nn.init.normal_(model.cond_in.weight, std=0.02)    # zero-init upstream: every path must carry signal (SURVEY 8d)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    rb = lambda *s: torch.randn(*s, device="cuda", generator=g).to(torch.bfloat16)   # noqa: E731
+    ids = torch.stack(torch.meshgrid(torch.arange(T), torch.arange(H), torch.arange(W), indexing="ij"), -1).reshape(1, Li, 3)
+    inp = dict(img=rb(B, Li, 64), img_ids=ids.float().repeat(B, 1, 1).cuda().to(torch.bfloat16), txt=rb(B, Lt, 4096),
+               txt_ids=torch.zeros(B, Lt, 3, device="cuda", dtype=torch.bfloat16), timesteps=torch.full((B,), 0.7, device="cuda", dtype=torch.bfloat16),
+               y_vec=rb(B, 768), cond=rb(B, Li, 68), guidance=None)
+    res = {"workload": f"MMDiT (flux) 256px inference shape: B={B}, L={Lt}+{Li}, C={C}, 24x128 heads, 19+38 blocks, fused_qkv=False, liger rope, bf16",
+           "algorithmic_tflop_per_step": tflop, "params_b": sum(p.numel() for p in model.parameters()) / 1e9}
+    with torch.no_grad():
+        out = model(**inp)                      # warm-up: packs weights, caches pe / RoPE tables
+        torch.cuda.synchronize()
+        res["finite"] = bool(torch.isfinite(out.float()).all())
+        res["out_shape"] = list(out.shape)
+        steps = 2
+        l0 = osb200.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = model(**inp)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        pk = peaks()
+        res.update(metric="denoise-steps/sec MMDiT 256px (B=3 CFG batch) bf16", value=1e3 / ms, unit="steps/s", ms_per_step=ms,
+                   tflops=tflop / (ms * 1e-3), frac_of_sustained_peak=tflop / (ms * 1e-3) / pk["sustained"],
+                   gpu_launches_per_step=(osb200.launch_count() - l0) // steps, peak_gb=torch.cuda.max_memory_allocated() / 2**30)
+        osb200.start_profile()
+        model(**inp)
+        fam = {}
+        for name, work, t in osb200.stop_profile():
+            f = fam.setdefault(name, [0, 0.0])
+            f[0] += 1
+            f[1] += t
+        res["families_ms"] = {k: {"launches": v[0], "ms": round(v[1], 2)} for k, v in fam.items()}
+    print(json.dumps(res), flush=True)
+
+
+def mmdit_leg(timeout_s: float = 180.0):
+    """Run the MMDiT leg in a child process (own CUDA context, hard time limit) and return its JSON object, or the reason it
+    produced none.  The parent has finished all of its own device work before this is called."""
+    try:
+        torch.cuda.empty_cache()
+        p = subprocess.run([sys.executable, os.path.abspath(__file__), "--leg", "mmdit"], capture_output=True, text=True,
+                           timeout=timeout_s, cwd=ROOT)
+        for ln in reversed(p.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": f"no result (rc {p.returncode}): " + (p.stderr or p.stdout)[-400:]}
+    except subprocess.TimeoutExpired:
+        return {"error": f"timed out after {timeout_s:.0f} s"}
+    except Exception as e:
+        return {"error": repr(e)[:300]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -379,6 +464,8 @@ def main():
                     help="replay the step as one CUDA graph (model.capture); default: on for sp, off otherwise")
     ap.add_argument("--no-graph", dest="graph", action="store_false")
     ap.add_argument("--no-library-baseline", action="store_true")
+    ap.add_argument("--leg", default=None, choices=["mmdit"], help="run ONE auxiliary leg in this process and print its JSON")
+    ap.add_argument("--no-mmdit", action="store_true", help="skip the MMDiT 256px leg (a child process of the N = 1 run)")
     ap.add_argument("--no-vae", action="store_true", help="skip the VAE leg (encode/decode fps of BASELINE.json's metric)")
     ap.add_argument("--profile-step", action="store_true",
                     help="after warm-up, bracket ONE step with cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`: "
@@ -389,6 +476,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.leg == "mmdit":
+        mmdit_leg_main()
+        return
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -554,6 +644,10 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         v, cores, sample = cpu_reference_step()
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    mmdit = None
+    if not args.no_mmdit and world == 1:
+        torch.cuda.synchronize()     # every number of this line is final before the child process touches the GPU
+        mmdit = mmdit_leg()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if args.parallel == "dp" else "strong",   # the --parallel mode the N > 1 runs of this line use (default sp: total work fixed)
@@ -564,7 +658,7 @@ def main():
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_out.numel() * 4,
                 "ms_per_step": ms_e2e / args.steps},
-        "roofline": roof, "cpu_baseline": cpu, "library_baseline": lib, "vae": vae,
+        "roofline": roof, "cpu_baseline": cpu, "library_baseline": lib, "vae": vae, "mmdit": mmdit,
     }
     if sp_check is not None:
         line["sp_check"] = sp_check
