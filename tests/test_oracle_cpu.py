@@ -145,6 +145,23 @@ def test_algorithmic_flop_model():
     import bench
 
     assert abs(bench.algorithmic_flops() / 1e12 - 36.13) < 0.01
+    # the MMDiT leg's shape and FLOP model: SURVEY.md 8d "MMDiT forward, per sample = 57 (24 C^2 L + 4 L^2 C)": 168.6 TF at 256px
+    c = bench.MMDIT_256PX
+    C, L = c["hidden_size"], 33 * 12 * 21 + 512
+    per_sample = (c["depth"] + c["depth_single_blocks"]) * (24.0 * C * C * L + 4.0 * L * L * C) / 1e12
+    assert abs(per_sample - 168.6) < 0.1 and C // c["num_heads"] == sum(c["axes_dim"]) == 128
+
+
+def test_bench_auxiliary_legs_fail_soft():
+    """The extra legs of the bench line report their own failure instead of raising: without a GPU the MMDiT child process
+    dies at `cuda.set_device` and the launcher returns the reason; the VAE CPU baseline is a pure host measurement."""
+    import bench
+
+    r = bench._vae_cpu_baseline()
+    assert "error" not in r and r["value"] > 0 and r["kind"] == "port" and r["unit"] == "frames/s"
+    if not torch.cuda.is_available():
+        m = bench.mmdit_leg(timeout_s=120)
+        assert set(m) == {"error"} and "rc 1" in m["error"]
 
 
 # ---- causal 3D VAE oracle pinned by reference-executed goldens --------------------------------------
