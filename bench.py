@@ -305,6 +305,7 @@ def vae_leg():
                          "algorithmic_conv_tflop": {"encode": ENC_TF, "decode": DEC_TF},
                          "mid_block_attention": "torch SDPA per frame prefix (library kernel; osb200 D=512 kernel pending)"}
         res["e2e"] = _vae_e2e(m, z, tuple(res["out_shape"]))
+        res["tiled"] = _vae_tiled(m, z)
         del m
         torch.cuda.empty_cache()
         res["cpu_baseline"] = _vae_cpu_baseline()
@@ -332,6 +333,30 @@ def _vae_e2e(m, z, shape):
                 "d2h_bytes": out_h.numel() * out_h.element_size()}
     except Exception as e:
         return {"error": repr(e)[:200]}
+
+
+def _vae_tiled(m, z):
+    """The same decode in the tiling mode the reference's VAE config ships (`configs/vae/inference/hunyuanvideo_vae.py`:
+    use_spatial_tiling + use_temporal_tiling: 256-px / 64-frame tiles, 25 % overlap, linear blends - SURVEY.md 8d asks for both
+    modes).  Tiles recompute their overlaps (~1.65x the convolution work at 720 x 1280) and normalise per tile, so this is a
+    different computation from the untiled decode, timed for reference.  Own try/except."""
+    try:
+        m.enable_tiling(True)
+        with torch.no_grad():
+            v = m.decode(z)                       # warm-up at the tile shapes
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            v = m.decode(z)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        return {"decode_ms": ms, "decode_fps": v.shape[2] / (ms * 1e-3), "out_shape": list(v.shape),
+                "mode": "spatial 256 px + temporal 64 frames, overlap 0.25 (the reference config's default)"}
+    except Exception as e:
+        return {"error": repr(e)[:200]}
+    finally:
+        m.enable_tiling(False)
 
 
 def _vae_cpu_baseline():
