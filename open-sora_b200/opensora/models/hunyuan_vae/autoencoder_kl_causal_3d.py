@@ -100,12 +100,12 @@ class AutoencoderKLCausal3D(nn.Module):
 
     def enable_temporal_parallel(self, process_group=None):
         """Shard the VAE by frames over `process_group` (one process per GPU; None switches it off).  Every rank passes the
-        SAME tensor to `encode` / `decode` and gets the whole result back.  Encoder: conv_in + down blocks on this rank's
-        frames, mid block + conv_out replicated on the gathered latent.  Decoder: conv_in + mid block run replicated, the up
-        blocks - over nine tenths of the decode's flops, more of its bytes - on this rank's run of frames with a two-frame causal halo from the
-        left neighbour and group-wide GroupNorm statistics (unet_causal_3d_blocks._TemporalShard), one gather at the end.
-        No reference counterpart (single-GPU VAE, tiled when short of memory); composes with spatial tiling, and temporal
-        tiles too short to shard are decoded replicated."""
+        SAME tensor to `encode` / `decode` and gets the whole result back; in between each rank works on its run of frames
+        in every layer: convolutions take a one- or two-frame causal halo from the left neighbour, GroupNorm statistics are
+        combined over the group, the mid block's frame-causal attention runs local queries against gathered keys / values
+        (unet_causal_3d_blocks._TemporalShard), and one gather at the end rebuilds the result.  No reference counterpart
+        (single-GPU VAE, tiled when short of memory; its channel-tensor-parallel policy is not reproduced); composes with
+        spatial tiling, and inputs too short to shard (fewer than 2 latent frames per rank) run replicated."""
         import torch.distributed as dist
 
         if process_group is not None and dist.get_world_size(process_group) == 1:

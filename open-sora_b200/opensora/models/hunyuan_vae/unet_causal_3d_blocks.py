@@ -26,7 +26,8 @@ class _TemporalShard:
       * normalises with GroupNorm statistics over ALL ranks' frames (per-rank mean / variance combined with their element
         counts - the parallel-variance identity, so no second pass over the activations), and
       * takes the two causal context frames it needs from its left neighbour (one point-to-point message per convolution)
-        instead of the replicate padding, which only rank 0 - the owner of the first frame - applies.
+        instead of the replicate padding, which only rank 0 - the owner of the first frame - applies;
+    and the mid block's frame-causal attention keeps its queries local and gathers keys / values (`_gather_frames`).
     The reference has no counterpart (its VAE runs on one GPU, tiled when memory is short: autoencoder_kl_causal_3d.py:
     454-560); results equal the un-sharded decode up to the rounding of the combined statistics.
 
@@ -254,22 +255,47 @@ class _MidAttention(nn.Module):
         osb = _osb()
         nb, T, H, W, C = x.shape
         hw = H * W
+        shard = _TemporalShard.group
         stats = osb.group_stats(x, self.group_norm.num_groups, self.group_norm.eps)
+        if shard is not None:
+            stats = _combine_group_stats(stats, T * hw * (C // self.group_norm.num_groups), self.group_norm.eps, shard)
         h = osb.vae_prep(x, stats=stats, gamma=self.group_norm.weight, beta=self.group_norm.bias,
                          groups=self.group_norm.num_groups, slack_bytes=0).view(nb * T * hw, C)
         q = osb.gemm(h, self.to_q.weight, self.to_q.bias).view(nb, 1, T * hw, C)
         k = osb.gemm(h, self.to_k.weight, self.to_k.bias).view(nb, 1, T * hw, C)
         v = osb.gemm(h, self.to_v.weight, self.to_v.bias).view(nb, 1, T * hw, C)
+        first = 0
+        if shard is not None:
+            # frame-sharded: queries stay local; keys / values of ALL ranks' frames are gathered (latent resolution: C = 512
+            # per token) and the causal prefix of local frame f ends at global frame first + f
+            k, v, first = _gather_frames(k, v, T, hw, shard)
         # Frame-causal attention (prepare_causal_attention_mask, :52-60): frame f attends to frames <= f, so the
         # mask is never materialised - one un-masked SDPA per query frame over the key prefix.  LIBRARY kernel
         # (torch SDPA, head_dim 512): the osb200 streaming attention for D=512 is the next kernel on this row.
         o = torch.empty_like(q)
         for f in range(T):
+            keys = (first + f + 1) * hw
             o[:, :, f * hw:(f + 1) * hw] = torch.nn.functional.scaled_dot_product_attention(
-                q[:, :, f * hw:(f + 1) * hw], k[:, :, :(f + 1) * hw], v[:, :, :(f + 1) * hw])
+                q[:, :, f * hw:(f + 1) * hw], k[:, :, :keys], v[:, :, :keys])
         out = osb.gemm(o.view(nb * T * hw, C), self.to_out[0].weight, self.to_out[0].bias, epilogue=osb.EPI_BIAS_GATE_RES,
                        residual=x.reshape(nb * T * hw, C))
         return out.view(nb, T, H, W, C)
+
+
+def _gather_frames(k, v, T: int, hw: int, group):
+    """k, v [nb, 1, T*hw, C] of this rank's T frames -> the same for the frames of all ranks in rank (= frame) order, and
+    the global index of this rank's first frame.  One all-gather of the frame counts, one var-len gather of k|v."""
+    import torch.distributed as dist
+
+    from opensora.acceleration.communications import gather_forward_split_backward_var_len
+
+    P, r = dist.get_world_size(group), dist.get_rank(group)
+    counts = [torch.zeros(1, dtype=torch.long, device=k.device) for _ in range(P)]
+    dist.all_gather(counts, torch.tensor([T], dtype=torch.long, device=k.device), group=group)
+    counts = [int(c) for c in counts]
+    kv = torch.cat((k, v), dim=1)                                    # [nb, 2, T*hw, C]
+    kv = gather_forward_split_backward_var_len(kv, 2, group, [c * hw for c in counts])
+    return kv[:, :1], kv[:, 1:], sum(counts[:r])
 
 
 class UNetMidBlockCausal3D(nn.Module):

@@ -66,10 +66,10 @@ class EncoderCausal3D(nn.Module):
             x = self.mid_block(x)
             return self.conv_out(x, norm=self.conv_norm_out, silu=True)
         # Frame-sharded encode (the mirror image of DecoderCausal3D's): rank r takes the pixel frames of its run of LATENT
-        # frames (rank 0: f c_0 - (f - 1), the others f c_r), so every temporally strided stage ends on a shard boundary;
-        # conv_in and the down blocks - all of the encode's high-resolution work - run on the local frames with the causal
-        # halo and group-wide GroupNorm statistics; the latent-resolution mid block (frame-causal attention over all frames)
-        # and conv_out run replicated on the gathered latent.
+        # frames (rank 0: f c_0 - (f - 1), the others f c_r), so every temporally strided stage ends on a shard boundary.
+        # Every layer runs on the local frames: convolutions with the causal halo from the left neighbour and group-wide
+        # GroupNorm statistics, the mid block's frame-causal attention with local queries against the gathered keys / values;
+        # one gather of the latent at the end.
         P, r = dist.get_world_size(group), dist.get_rank(group)
         counts = frame_partition(latent_frames, P)
         pixel = [f * c - (f - 1 if q == 0 else 0) for q, c in enumerate(counts)]
@@ -79,10 +79,10 @@ class EncoderCausal3D(nn.Module):
             x = self.conv_in(x)
             for blk in self.down_blocks:
                 x = blk(x)
-        assert x.shape[1] == counts[r], (x.shape, counts, r)
-        x = gather_forward_split_backward_var_len(x, 1, group, counts)
-        x = self.mid_block(x)
-        return self.conv_out(x, norm=self.conv_norm_out, silu=True)
+            assert x.shape[1] == counts[r], (x.shape, counts, r)
+            x = self.mid_block(x)
+            x = self.conv_out(x, norm=self.conv_norm_out, silu=True)
+        return gather_forward_split_backward_var_len(x, 1, group, counts)
 
 
 class DecoderCausal3D(nn.Module):
@@ -112,23 +112,25 @@ class DecoderCausal3D(nn.Module):
         self.shard_group = None   # set by AutoencoderKLCausal3D.enable_temporal_parallel
 
     def forward(self, sample):  # NDHWC bf16 latent
-        x = self.conv_in(sample)
-        x = self.mid_block(x)
         group = self.shard_group
         # fewer than 2 latent frames per rank (the causal halo is 2 frames deep): every rank decodes the whole (tile of the)
         # latent - same result on every rank, no exchange
-        if group is None or x.shape[1] < 2 * dist.get_world_size(group):
+        if group is None or sample.shape[1] < 2 * dist.get_world_size(group):
+            x = self.conv_in(sample)
+            x = self.mid_block(x)
             for blk in self.up_blocks:
                 x = blk(x)
             return self.conv_out(x, norm=self.conv_norm_out, silu=True)
-        # Frame-sharded decode: conv_in + the mid block (latent resolution, frame-causal attention over all frames: under a tenth
-        # of the decode's flops) run replicated, then each rank keeps its run of latent frames through the up blocks - where the
-        # activations grow 4 x 8 x 8 fold - and the pixel frames are gathered once at the end.
+        # Frame-sharded decode: each rank keeps its run of latent frames through EVERY layer - conv_in, the mid block (frame-
+        # causal attention: local queries against the gathered keys / values of the earlier frames), the up blocks, where
+        # the activations grow 4 x 8 x 8 fold, and conv_out - and the pixel frames are gathered once at the end.
         P, r = dist.get_world_size(group), dist.get_rank(group)
-        counts = frame_partition(x.shape[1], P)
+        counts = frame_partition(sample.shape[1], P)
         first = sum(counts[:r])
-        x = x[:, first:first + counts[r]].contiguous()
-        with temporal_shard(group):
+        x = sample[:, first:first + counts[r]].contiguous()
+        with temporal_shard(group, start=first):
+            x = self.conv_in(x)
+            x = self.mid_block(x)
             for blk in self.up_blocks:
                 x = blk(x)
             x = self.conv_out(x, norm=self.conv_norm_out, silu=True)
