@@ -1,11 +1,13 @@
 """The tensor-producing half of `opensora/utils/inference.py` that sits between the user's request and the denoiser:
 `SamplingMethod` (:16-18), `modify_option_to_t2i` (:43-55), `add_noise_to_ref` (:210-213), `collect_references_batch`
 (:216-280) and `prepare_inference_condition` (:283-351) - the image / video conditioning format (`masks`, `masked_ref`)
-that `I2VDenoiser.denoise` packs into `cond`.  CSV handling, file naming, saving and prompt refinement (:21-40, :58-207)
-are I/O around the pipeline and out of scope."""
+that `I2VDenoiser.denoise` packs into `cond` - plus the prompt suffix conventions the text conditioning was trained with
+(`add_fps_info_to_text` :186-196, `add_motion_score_to_text` :199-207).  CSV handling, file naming, saving and LLM prompt
+refinement (:21-40, :58-163) are I/O around the pipeline and out of scope."""
 from __future__ import annotations
 
 import copy
+import re
 from enum import Enum
 
 import torch
@@ -29,6 +31,36 @@ def modify_option_to_t2i(sampling_option, distilled: bool = False, img_resolutio
     opt.guidance = 4.0
     opt.resized_resolution = sampling_option.resolution
     return opt
+
+
+def check_fps_added(sentence: str) -> bool:
+    """Does the prompt already end with "<n> FPS."?"""
+    return re.search(r"\d+ FPS\.$", sentence) is not None
+
+
+def ensure_sentence_ends_with_period(sentence: str) -> str:
+    sentence = sentence.strip()
+    return sentence if sentence.endswith(".") else sentence + "."
+
+
+def add_fps_info_to_text(text: list[str], fps: int = 16) -> list[str]:
+    """Every prompt ends with a period and then " <fps> FPS." (once)."""
+    out = []
+    for prompt in text:
+        prompt = ensure_sentence_ends_with_period(prompt)
+        out.append(prompt if check_fps_added(prompt) else f"{prompt} {fps} FPS.")
+    return out
+
+
+def add_motion_score_to_text(text: list[str], motion_score: int | str, refine_prompts=None) -> list[str]:
+    """Append "<score> motion score." to every prompt.  "dynamic" asks an LLM for a per-prompt score upstream
+    (`opensora/utils/prompt_refine.py`, network access): pass that callable as `refine_prompts` to get the same behaviour."""
+    if motion_score == "dynamic":
+        if refine_prompts is None:
+            raise NotImplementedError('motion_score="dynamic" needs `refine_prompts(text, type="motion_score")` (an LLM call upstream)')
+        scores = refine_prompts(text, type="motion_score")
+        return [f"{t} {scores[i]}." for i, t in enumerate(text)]
+    return [f"{t} {motion_score} motion score." for t in text]
 
 
 def add_noise_to_ref(masked_ref: torch.Tensor, masks: torch.Tensor, t: float, sigma_min: float = 1e-5):

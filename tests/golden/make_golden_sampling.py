@@ -70,6 +70,11 @@ def pipeline(S):
     t2i = I.modify_option_to_t2i(S.SamplingOption(resolution="256px", aspect_ratio="16:9", num_frames=33, guidance=7.5), distilled=True,
                                  img_resolution="768px")
     meta["t2i"] = [t2i.height, t2i.width, t2i.num_frames, t2i.guidance, t2i.method.value, t2i.resized_resolution]
+    prompts = ["a cat", "a dog runs.  ", "waves at 24 FPS.", "x 16 FPS"]
+    meta["prompts"] = prompts
+    meta["fps_text"] = I.add_fps_info_to_text(list(prompts), fps=24)
+    meta["fps_text_default"] = I.add_fps_info_to_text(list(prompts))
+    meta["motion_text"] = I.add_motion_score_to_text(list(prompts), 4)
     meta["guidance_i2v"] = S.I2VDenoiser().prepare_guidance(["a", "b"], {}, "cpu", torch.float32, neg=None, guidance_img=3.0)[0]
     meta["guidance_i2v_neg"] = S.I2VDenoiser().prepare_guidance(["a"], {}, "cpu", torch.float32, neg=["n"], guidance_img=3.0)[0]
 

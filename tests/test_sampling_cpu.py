@@ -106,6 +106,13 @@ def test_options_aspect_tables_and_guidance_prompts():
     assert S.I2VDenoiser().prepare_guidance(["a"], {}, "cpu", torch.float32, neg=["n"], guidance_img=3.0)[0] == meta["guidance_i2v_neg"]
     assert S.DistilledDenoiser().prepare_guidance(["a"], {}, "cpu", torch.float32) == (["a"], {})
     assert set(S.SamplingMethodDict) == {S.SamplingMethod.I2V, S.SamplingMethod.DISTILLED}
+    # prompt suffix conventions (fps / motion score) of the request format
+    assert I.add_fps_info_to_text(list(meta["prompts"]), fps=24) == meta["fps_text"]
+    assert I.add_fps_info_to_text(list(meta["prompts"])) == meta["fps_text_default"]
+    assert I.add_motion_score_to_text(list(meta["prompts"]), 4) == meta["motion_text"]
+    assert I.add_motion_score_to_text(["a"], "dynamic", refine_prompts=lambda t, type: ["7 motion score"]) == ["a 7 motion score."]
+    with pytest.raises(NotImplementedError):
+        I.add_motion_score_to_text(["a"], "dynamic")
 
 
 def test_model_inputs_and_conditioning_format():
