@@ -76,3 +76,4 @@ def build_module(module: dict | nn.Module | None, builder: Registry, **kwargs) -
 
 MODELS = Registry("model", locations=["opensora.models"])
 DATASETS = Registry("dataset", locations=["opensora.datasets"])
+SCHEDULERS = Registry("scheduler", locations=["opensora.schedulers"])   # v1.2 name; the v2.0 tree has no scheduler registry

@@ -55,3 +55,31 @@ def denoise(model, img, timesteps, guidance, guidance_img, masks, masked_ref, te
         pred = u2_ + ig * (u_ - u2_) + tg * (c_ - u_)
         img = img + (tp - tc) * torch.cat([pred, pred, pred], 0)
     return img[: len(img) // 3]
+
+
+# ---- STDiT3's sampler (Open-Sora v1.2 `schedulers/rf`): NOT in the reference tree -> restatement of SURVEY.md Appendix A,
+# ---- "RF sampler" row; PARITY UNPINNED (no reference source or vector exists for it here) --------------------------------
+def rflow_timestep_transform(t, height, width, num_frames, num_timesteps=1000):
+    """t' = r t / (1 + (r - 1) t),  r = sqrt(H W / 512^2) * sqrt(frames // 17 * 5)  (r_time = 1 for a single frame)."""
+    t = t / num_timesteps
+    r = math.sqrt(height * width / (512 * 512)) * (1.0 if num_frames == 1 else math.sqrt(num_frames // 17 * 5))
+    return r * t / (1 + (r - 1) * t) * num_timesteps
+
+
+def rflow_sample(model, z, y, y_null, mask=None, steps=30, cfg_scale=7.0, transform=None, **model_kw):
+    """timesteps_i = (1 - i/N) 1000 (optionally transformed); per step z_in = cat[z, z], pred = model(z_in, cat[t, t],
+    y = cat[y, y_null]).chunk(2, dim=1)[0]; v = v_u + s (v_c - v_u); z += v (t_i - t_{i+1}) / 1000."""
+    B = z.shape[0]
+    ts = [(1.0 - i / steps) * 1000.0 for i in range(steps)]
+    if transform is not None:
+        ts = [rflow_timestep_transform(t, *transform) for t in ts]
+    kw = {k: (torch.cat((v, v), 0) if isinstance(v, torch.Tensor) and v.shape[:1] == (B,) else v) for k, v in model_kw.items()}
+    if mask is not None:
+        kw["mask"] = torch.cat((mask, mask), 0)
+    for i, t in enumerate(ts):
+        tv = torch.full((2 * B,), t, dtype=torch.float32)
+        pred = model(torch.cat((z, z), 0), tv, y=torch.cat((y, y_null), 0), **kw).chunk(2, dim=1)[0]
+        vc, vu = pred.chunk(2, dim=0)
+        t_next = ts[i + 1] if i + 1 < len(ts) else 0.0
+        z = z + (vu + cfg_scale * (vc - vu)) * ((t - t_next) / 1000.0)
+    return z

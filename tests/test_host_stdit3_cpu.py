@@ -114,3 +114,31 @@ def test_sequence_parallel_model_world2_is_bit_identical():
     ret = mgr.dict()
     mp.spawn(_sp_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret.get(0) is True and ret.get(1) is True
+
+
+def test_rflow_sampler_drives_the_model(fake_osb):
+    """The v1.2 sampling loop (`opensora/schedulers/rf.py`: CFG batch of 2 with the model's own null caption, velocity half of
+    the `pred_sigma` output, fused combine + Euler update) around the REAL host-side STDiT3, against the oracle loop around the
+    fp32 oracle model: three steps, ragged caption mask."""
+    from opensora.schedulers import RFLOW
+    from oracle import sampling_oracle as S
+
+    prod, oracle, cfg = _pair()
+    inp = _inputs(cfg, 2, 4, 8, 8, lens=[cfg.model_max_length, 11])
+    B = 2
+    y_null = prod.y_embedder.y_embedding.detach()[None, None].repeat(B, 1, 1, 1)
+    extra = dict(fps=inp["fps"], height=inp["height"], width=inp["width"])
+    z0 = inp["x"].to(torch.bfloat16)
+    with torch.no_grad():
+        ref = S.rflow_sample(lambda x, t, y, **kw: oracle(x, t, y, **kw), z0.float(), inp["y"], y_null.float(), mask=inp["mask"],
+                             steps=3, cfg_scale=4.0, **extra)
+        out = RFLOW(num_sampling_steps=3, cfg_scale=4.0).sample(prod, z0, inp["y"], y_null, mask=inp["mask"], additional_args=extra)
+        # the reference-precision floor of the same loop: the oracle model in bf16, latent rounded to bf16 after every step
+        ob = oracle.to(torch.bfloat16)
+        noise = S.rflow_sample(lambda x, t, y, **kw: ob(x.to(torch.bfloat16).float(), t, y, **kw).float(), z0.float(), inp["y"],
+                               y_null.float(), mask=inp["mask"], steps=3, cfg_scale=4.0, **extra)
+    assert out.shape == z0.shape and out.dtype == torch.bfloat16
+    r, rn = rel_l2(out, ref), rel_l2(noise, ref)
+    # guidance amplifies the model's bf16 error (v = v_u + 4 (v_c - v_u)); a wrong branch order / sign / dt would be O(1)
+    assert r < max(1.5 * rn, 1e-2) and r < 6e-2, (r, rn)
+    assert [c[0] for c in fake_osb.calls].count("cfg_euler") == 3

@@ -185,3 +185,42 @@ def test_prepare_api_end_to_end_vs_reference(fake_osb, monkeypatch, scenario):
     assert r < (1e-3 if distilled else 2e-2), (name, r)
     if not distilled:
         assert [c[0] for c in fake_osb.calls].count("cfg_euler") == opt.num_steps   # one fused update per step
+
+
+# ---- STDiT3's own sampler (v1.2 RFLOW; absent from the reference tree, restated from SURVEY.md Appendix A: unpinned) ------------
+def _toy_stdit(x, timestep, y, mask=None, fps=None, height=None, width=None, **kw):
+    """[2B, C, T, H, W] -> [2B, 2C, T, H, W] fp32 (velocity | sigma halves), depending on every input."""
+    f = x.float()
+    cap = (y.float() * (1.0 if mask is None else mask.float()[:, None, :, None])).mean(dim=(1, 2, 3))[:, None, None, None, None]
+    v = torch.tanh(0.8 * f + cap) * (0.5 + timestep.float()[:, None, None, None, None] / 1000.0) + 0.01 * fps.float()[:, None, None, None, None]
+    return torch.cat((v, 0.1 * f), dim=1)
+
+
+@pytest.mark.parametrize("transform", [False, True])
+def test_rflow_sampler_host_logic_vs_oracle(fake_osb, transform):
+    from opensora.registry import SCHEDULERS
+    from opensora.schedulers import RFLOW, timestep_transform
+    from oracle import sampling_oracle as O
+
+    assert SCHEDULERS.get("rflow") is RFLOW
+    g = torch.Generator().manual_seed(9)
+    B, C, T, H, W, L = 2, 4, 5, 6, 8, 7
+    z = torch.randn(B, C, T, H, W, generator=g)
+    y, y_null = torch.randn(B, 1, L, 16, generator=g), torch.randn(1, 1, L, 16, generator=g).repeat(B, 1, 1, 1)
+    mask = torch.ones(B, L)
+    mask[1, 4:] = 0
+    extra = dict(fps=torch.full((B,), 24.0), height=torch.full((B,), 360.0), width=torch.full((B,), 640.0))
+    ref = O.rflow_sample(_toy_stdit, z.to(torch.bfloat16).float(), y, y_null, mask=mask, steps=8, cfg_scale=7.0,
+                         transform=(360.0, 640.0, 51) if transform else None, **extra)
+    sch = RFLOW(num_sampling_steps=8, cfg_scale=7.0, use_timestep_transform=transform)
+    out = sch.sample(_toy_stdit, z.to(torch.bfloat16), y, y_null, mask=mask, additional_args=dict(extra, num_frames=torch.full((B,), 51)))
+    r = float((out.float() - ref).norm() / ref.norm())
+    assert out.dtype == torch.bfloat16 and r < 2e-2, r
+    assert [c[0] for c in fake_osb.calls].count("cfg_euler") == 8          # one fused combine + Euler update per step
+    # the schedule transform: identity at r = 1 (512 x 512 image), fixed points 0 and 1000, closed form at a known point
+    t = torch.tensor([0.0, 250.0, 1000.0])
+    assert torch.allclose(timestep_transform(t, 512.0, 512.0, torch.tensor([1])), t)
+    tt = timestep_transform(t, 360.0, 640.0, torch.tensor([51]))
+    r_ = (360 * 640 / 512**2) ** 0.5 * (51 // 17 * 5) ** 0.5
+    assert torch.allclose(tt, torch.tensor([0.0, 1000 * r_ * 0.25 / (1 + (r_ - 1) * 0.25), 1000.0]), rtol=1e-5)
+    assert abs(float(tt[1]) - O.rflow_timestep_transform(250.0, 360.0, 640.0, 51)) < 1e-3
